@@ -1,0 +1,261 @@
+"""ctypes binding of ``libbdg.so`` -- the thin layer between the Python surface and the C ABI
+declared in ``include/bdg.h``.
+
+No fallback: if the library is missing or no CUDA device is usable, the calls raise.  Return
+codes are mapped to the exception types the reference raises in the same situation
+(``bodge/hamiltonian.py:122,170``, ``bodge/lattice.py:106``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbdg.so")
+
+OK, E_INVALID, E_CUDA, E_NOT_NEIGHBOUR, E_NOT_HERMITIAN, E_OUT_OF_BOUNDS, E_NO_DEVICE = range(7)
+X0_PROBE, X0_RADEMACHER = 0, 1
+MU_PER_COLUMN, MU_SUM = 0, 1
+KERNEL_AUTO, KERNEL_DMMA, KERNEL_FMA = 0, 1, 2
+KERNELS = {"auto": KERNEL_AUTO, "dmma": KERNEL_DMMA, "fma": KERNEL_FMA}
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> argument types (every function returns int unless noted); mirrors include/bdg.h.
+SIGNATURES = {
+    "bdg_abi_version": [],
+    "bdg_device_count": [C.POINTER(C.c_int)],
+    "bdg_destroy": [_vp],
+    "bdg_set_stream": [_vp, _vp],
+    "bdg_sync": [_vp],
+    "bdg_device_bytes": [_vp, _i64p],
+    "bdg_pinned_alloc": [C.c_int64, C.POINTER(_vp)],
+    "bdg_pinned_free": [_vp],
+    "bdg_create_cubic": [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)],
+    "bdg_create_generic": [C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.POINTER(_vp)],
+    "bdg_skeleton_sizes": [_vp, _i64p, _i64p],
+    "bdg_lookup": [_vp, C.c_int64, _vp, _vp, _vp, _i64p],
+    "bdg_scatter": [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_double, _f64p, _i64p],
+    "bdg_clear": [_vp],
+    "bdg_export_bsr": [_vp, C.c_int, _i64p, _vp, _vp, _vp],
+    "bdg_import_data": [_vp, _vp],
+    "bdg_norm_inf": [_vp, _f64p],
+    "bdg_cheb_begin": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int],
+    "bdg_cheb_steps": [_vp, C.c_int32, C.POINTER(C.c_float)],
+    "bdg_cheb_available": [_vp, C.POINTER(C.c_int32)],
+    "bdg_cheb_moments_read": [_vp, C.c_int32, C.c_int, _vp, C.c_int],
+    "bdg_cheb_moments": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int32, C.c_int, _vp, C.c_int],
+    "bdg_cheb_vectors": [_vp, C.c_int, _vp],
+    "bdg_cheb_info": [_vp, _i64p, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64p],
+    "bdg_cheb_end": [_vp],
+}
+
+_lib = None
+
+
+def load():
+    """Load ``libbdg.so`` (once).  Raises ``RuntimeError`` if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m bodge_b200.build` "
+            "(bodge_b200 has no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.bdg_last_error.argtypes = []
+    lib.bdg_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().bdg_last_error().decode("utf-8", "replace")
+
+
+_EXC = {
+    E_INVALID: ValueError,
+    E_CUDA: RuntimeError,
+    E_NOT_NEIGHBOUR: IndexError,
+    E_NOT_HERMITIAN: RuntimeError,
+    E_OUT_OF_BOUNDS: ValueError,
+    E_NO_DEVICE: RuntimeError,
+}
+
+
+def check(rc: int):
+    if rc != OK:
+        raise _EXC.get(rc, RuntimeError)(last_error())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = load().bdg_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _as(a, dtype, shape_tail=()):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape_tail and a.shape[1:] != shape_tail:
+        raise ValueError(f"expected trailing shape {shape_tail}, got {a.shape[1:]}")
+    return a
+
+
+class System:
+    """Owner of one ``bdg_t`` handle (one Hamiltonian on one GPU)."""
+
+    def __init__(self, handle, n_sites, n_blocks, device):
+        self._h = handle
+        self.n_sites = n_sites
+        self.n_blocks = n_blocks
+        self.device = device
+
+    # -- construction / destruction ------------------------------------------------------
+    @classmethod
+    def _finish(cls, lib, handle, device):
+        n, nb = C.c_int64(), C.c_int64()
+        check(lib.bdg_skeleton_sizes(handle, C.byref(n), C.byref(nb)))
+        return cls(handle, n.value, nb.value, device)
+
+    @classmethod
+    def cubic(cls, shape, device=0):
+        lib = load()
+        h = _vp()
+        check(lib.bdg_create_cubic(device, int(shape[0]), int(shape[1]), int(shape[2]), C.byref(h)))
+        return cls._finish(lib, h, device)
+
+    @classmethod
+    def generic(cls, n_sites, pair_i, pair_j, device=0):
+        lib = load()
+        pi, pj = _as(pair_i, np.int32), _as(pair_j, np.int32)
+        h = _vp()
+        check(lib.bdg_create_generic(device, int(n_sites), len(pi), _ptr(pi), _ptr(pj), C.byref(h)))
+        return cls._finish(lib, h, device)
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.bdg_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def set_stream(self, stream_ptr: int | None):
+        check(load().bdg_set_stream(self._h, _vp(stream_ptr) if stream_ptr else None))
+
+    def sync(self):
+        check(load().bdg_sync(self._h))
+
+    def device_bytes(self) -> int:
+        b = C.c_int64()
+        check(load().bdg_device_bytes(self._h, C.byref(b)))
+        return b.value
+
+    # -- assembly -----------------------------------------------------------------------------
+    def lookup(self, i, j) -> np.ndarray:
+        i, j = _as(i, np.int32), _as(j, np.int32)
+        k = np.empty(len(i), dtype=np.int64)
+        bad = C.c_int64(-1)
+        check(load().bdg_lookup(self._h, len(i), _ptr(i), _ptr(j), _ptr(k), C.byref(bad)))
+        return k
+
+    def scatter(self, h_i, h_j, h_val, p_i, p_j, p_val, herm_tol=1e-6) -> float:
+        h_i, h_j = _as(h_i, np.int32), _as(h_j, np.int32)
+        p_i, p_j = _as(p_i, np.int32), _as(p_j, np.int32)
+        h_val = _as(np.asarray(h_val).reshape(-1, 2, 2), np.complex128, (2, 2))
+        p_val = _as(np.asarray(p_val).reshape(-1, 2, 2), np.complex128, (2, 2))
+        if not (len(h_i) == len(h_j) == len(h_val) and len(p_i) == len(p_j) == len(p_val)):
+            raise ValueError("index and value arrays differ in length")
+        dev, bad = C.c_double(0.0), C.c_int64(-1)
+        check(load().bdg_scatter(self._h, len(h_i), _ptr(h_i), _ptr(h_j), _ptr(h_val), len(p_i), _ptr(p_i),
+                                 _ptr(p_j), _ptr(p_val), float(herm_tol), C.byref(dev), C.byref(bad)))
+        return dev.value
+
+    def clear(self):
+        check(load().bdg_clear(self._h))
+
+    def export_bsr(self, eliminate_zeros: bool):
+        lib = load()
+        nb = C.c_int64()
+        check(lib.bdg_export_bsr(self._h, int(eliminate_zeros), C.byref(nb), None, None, None))
+        indptr = np.empty(self.n_sites + 1, dtype=np.int32)
+        indices = np.empty(nb.value, dtype=np.int32)
+        data = np.empty((nb.value, 4, 4), dtype=np.complex128)
+        check(lib.bdg_export_bsr(self._h, int(eliminate_zeros), C.byref(nb), _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def import_data(self, data):
+        data = _as(data, np.complex128)
+        if data.shape != (self.n_blocks, 4, 4):
+            raise ValueError(f"expected data of shape {(self.n_blocks, 4, 4)}, got {data.shape}")
+        check(load().bdg_import_data(self._h, _ptr(data)))
+
+    def norm_inf(self) -> float:
+        v = C.c_double()
+        check(load().bdg_norm_inf(self._h, C.byref(v)))
+        return v.value
+
+    # -- Chebyshev engine ---------------------------------------------------------------------
+    def cheb_begin(self, *, probe_rows=None, n_random=0, seed=0, col_offset=0, scale, kernel="auto"):
+        lib = load()
+        if probe_rows is not None:
+            rows = _as(probe_rows, np.int64)
+            check(lib.bdg_cheb_begin(self._h, X0_PROBE, len(rows), _ptr(rows), 0, 0, float(scale), KERNELS[kernel]))
+        else:
+            check(lib.bdg_cheb_begin(self._h, X0_RADEMACHER, int(n_random), None, C.c_uint64(int(seed)),
+                                     int(col_offset), float(scale), KERNELS[kernel]))
+
+    def cheb_steps(self, n_steps: int, timed: bool = False):
+        ms = C.c_float(0.0)
+        check(load().bdg_cheb_steps(self._h, int(n_steps), C.byref(ms) if timed else None))
+        return ms.value if timed else None
+
+    def cheb_available(self) -> int:
+        n = C.c_int32()
+        check(load().bdg_cheb_available(self._h, C.byref(n)))
+        return n.value
+
+    def cheb_read(self, n_moments: int, n_cols: int, summed: bool = False, device_ptr: int | None = None):
+        """Moments as ``[n_moments, n_cols]`` (or ``[n_moments]`` summed over columns); with
+        ``device_ptr`` they are written to that device address instead and ``None`` is returned."""
+        lib = load()
+        if device_ptr is not None:
+            check(lib.bdg_cheb_moments_read(self._h, int(n_moments), int(summed), _vp(device_ptr), 1))
+            return None
+        out = np.empty((n_moments,) if summed else (n_moments, n_cols), dtype=np.float64)
+        check(lib.bdg_cheb_moments_read(self._h, int(n_moments), int(summed), _ptr(out), 0))
+        return out
+
+    def cheb_vectors(self, n_cols: int, which: int = 0) -> np.ndarray:
+        out = np.empty((4 * self.n_sites, n_cols), dtype=np.complex128)
+        check(load().bdg_cheb_vectors(self._h, int(which), _ptr(out)))
+        return out
+
+    def cheb_info(self) -> dict:
+        nb, by, la = C.c_int64(), C.c_int64(), C.c_int64()
+        pw, npan = C.c_int32(), C.c_int32()
+        check(load().bdg_cheb_info(self._h, C.byref(nb), C.byref(by), C.byref(pw), C.byref(npan), C.byref(la)))
+        return dict(n_blocks=nb.value, bytes_per_step=by.value, panel_width=pw.value, n_panels=npan.value,
+                    launches=la.value)
+
+    def cheb_end(self):
+        check(load().bdg_cheb_end(self._h))

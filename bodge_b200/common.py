@@ -1,0 +1,55 @@
+"""Vocabulary shared by the whole package: numeric imports, type aliases, Pauli matrices.
+
+Mirrors the names exported by the reference's ``bodge/common.py:1-61`` so user scripts that
+do ``from bodge import *`` keep working after switching the import to ``bodge_b200``: the
+2x2 ``complex128`` matrices below are the *input* vocabulary of the hot path (every
+``H[i, j]`` / ``Δ[i, j]`` the user writes is built from them).
+"""
+
+import numpy as np
+import numpy.typing as npt
+import scipy.linalg as la
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+from beartype import beartype as typecheck
+from beartype.typing import Callable, Iterator
+
+# Lattice coordinates and flat indices.
+Index = int
+Coord = tuple[int, int, int]
+Indices = tuple[Index, Index]
+Coords = tuple[Coord, Coord]
+
+# Matrix containers handed to / returned from the public API.
+Matrix = npt.NDArray[np.float64] | npt.NDArray[np.complex128]
+CooMatrix = sp.coo_matrix
+DiaMatrix = sp.dia_matrix
+BsrMatrix = sp.bsr_matrix
+CsrMatrix = sp.csr_matrix
+CscMatrix = sp.csc_matrix
+SpMatrix = sp.spmatrix
+
+π = np.pi
+pi = π
+
+
+def _pauli(a, b, c, d) -> Matrix:
+    return np.array([[a, b], [c, d]], dtype=np.complex128)
+
+
+# Spin matrices (identity + the three Pauli matrices) and their i-multiples.
+σ0: Matrix = _pauli(1, 0, 0, 1)
+σ1: Matrix = _pauli(0, 1, 1, 0)
+σ2: Matrix = _pauli(0, -1j, 1j, 0)
+σ3: Matrix = _pauli(1, 0, 0, -1)
+σ = np.stack([σ1, σ2, σ3])
+
+jσ0: Matrix = 1j * σ0
+jσ1: Matrix = 1j * σ1
+jσ2: Matrix = 1j * σ2
+jσ3: Matrix = 1j * σ3
+jσ = np.stack([jσ1, jσ2, jσ3])
+
+# ASCII spellings.
+sigma0, sigma1, sigma2, sigma3, sigma = σ0, σ1, σ2, σ3, σ
+jsigma0, jsigma1, jsigma2, jsigma3, jsigma = jσ0, jσ1, jσ2, jσ3, jσ

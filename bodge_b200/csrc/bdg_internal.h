@@ -1,0 +1,115 @@
+// Internal declarations shared by the libbdg translation units (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "bdg.h"
+
+// ---- error plumbing ---------------------------------------------------------------------
+void bdg_set_error(const char *fmt, ...);
+
+#define BDG_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t err__ = (expr);                                                         \
+        if (err__ != cudaSuccess) {                                                         \
+            bdg_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                          cudaGetErrorString(err__));                                       \
+            return BDG_E_CUDA;                                                              \
+        }                                                                                   \
+    } while (0)
+
+#define BDG_TRY(expr)                                                                       \
+    do {                                                                                    \
+        int rc__ = (expr);                                                                  \
+        if (rc__ != BDG_OK) return rc__;                                                    \
+    } while (0)
+
+#define BDG_REQUIRE(cond, ...)                                                              \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            bdg_set_error(__VA_ARGS__);                                                     \
+            return BDG_E_INVALID;                                                           \
+        }                                                                                   \
+    } while (0)
+
+// ---- device buffers -----------------------------------------------------------------------
+// Thin owner of one cudaMalloc'd array; tracks bytes per handle.
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct bdg_system;
+int dev_alloc(bdg_system *sys, DevBuf &buf, size_t bytes);
+void dev_free(bdg_system *sys, DevBuf &buf);
+
+// ---- BSR structure on the device ---------------------------------------------------------
+// data layout == scipy bsr_matrix.data: [nb][4][4] complex128 (re, im interleaved), 256 B/block.
+struct BsrDev {
+    int64_t n_sites = 0;
+    int64_t n_blocks = 0;
+    DevBuf indptr;   // int32 [n_sites + 1]
+    DevBuf indices;  // int32 [n_blocks]   ascending within a row
+    DevBuf brow;     // int32 [n_blocks]   block row of every block (skeleton only)
+    DevBuf data;     // double2 [n_blocks * 16]
+};
+
+// ---- Chebyshev state ----------------------------------------------------------------------
+struct ChebState {
+    bool active = false;
+    int kernel = BDG_KERNEL_DMMA;
+    int32_t n_cols = 0;       // user columns on this GPU
+    int32_t panel_width = 8;  // PW: columns per panel (1, 2, 4 or 8)
+    int32_t n_panels = 0;
+    double scale = 1.0;
+    int32_t steps_done = 0;   // recursion steps after T_1 (T_{steps_done+1} is current)
+    int32_t dot_capacity = 0; // steps for which dot storage exists
+    // Vectors: [panel][site][col_in_panel][alpha] complex128; cur = T_n, prev = T_{n-1}.
+    DevBuf vec[2];
+    int cur = 0;
+    // dots[(step * 2 + which) * n_panels * PW + panel * PW + c]; which 0 = <T_n,T_n>, 1 = <T_{n+1},T_n>
+    DevBuf dots;
+    DevBuf partials;  // per-CTA partial dot products of the step in flight
+    DevBuf tickets;   // uint32 [n_panels] arrival counters (last CTA reduces)
+    DevBuf mu_tmp;    // staging for moment read-out
+    int grid_x = 0;
+    int64_t launches = 0;
+};
+
+struct bdg_system {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t dev_bytes = 0;
+
+    BsrDev skel;           // full skeleton, values as scattered so far
+    BsrDev packed;         // after eliminate_zeros (built lazily)
+    bool packed_valid = false;
+
+    DevBuf scratch_i32[4];  // reusable scratch (counts, scans, flags, positions)
+    DevBuf stage[10];       // uploaded entry lists: {i, j, values, k1, k2} x {hopping, pairing}
+    DevBuf scalars;         // small device scalars (first_bad, max_dev, ...)
+    void *host_scalars = nullptr;  // pinned mirror
+
+    ChebState cheb;
+};
+
+// scan.cu
+int exclusive_scan_i32(bdg_system *sys, const int32_t *in, int32_t *out, int64_t n,
+                       int32_t *total_dev /* device, may be null */);
+
+// assemble.cu
+int build_packed(bdg_system *sys);
+int ensure_scratch(bdg_system *sys, int which, size_t bytes);
+
+// cheb.cu
+void cheb_release(bdg_system *sys);     // free all Chebyshev buffers
+void cheb_deactivate(bdg_system *sys);  // matrix changed: recursion state is stale, keep buffers
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

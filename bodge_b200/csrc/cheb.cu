@@ -1,0 +1,544 @@
+// Chebyshev / kernel-polynomial engine: fused block-sparse SpMM + three-term update + moment
+// dot products, one HBM pass per step.
+//
+//   T_{n+1} = alpha * H * T_n - beta * T_{n-1}      (alpha = 2/a, beta = 1;  first step: 1/a, 0)
+//   d0 = <T_n, T_n>,  d1 = <T_{n+1}, T_n>           (per column; give mu_2n and mu_2n+1)
+//
+// There is no reference code for this; the arithmetic it must reproduce is scipy's
+// bsr_matvecs on the reference's matrix("bsr") driven by the textbook recursion (oracle/).
+//
+// Data layout in HBM
+//   matrix : the compacted BSR exactly as exported (indptr int32, indices int32, data [nb][4][4]
+//            complex128, 256 B per block, row-major inside the block).
+//   vectors: column panels of PW in {1,2,4,8} columns; inside a panel one contiguous record per
+//            site, [site][column][alpha] complex128 = 64*PW bytes (512 B at PW = 8).  A warp
+//            reads or writes a whole record with one 128-bit access per lane.
+//
+// Kernel (cheb_step_dmma): one warp per block row.  The 4x4 complex block times the 4xPW complex
+// record is the real product [[Br,-Bi],[Bi,Br]] (8x8) x [Xr;Xi] (8xPW): exactly two FP64
+// m8n8k4 warp-level MMAs, with lane l fetching block element l%16 and record element l -- both
+// fully coalesced, no shared-memory staging, ~40 registers, so 64 resident warps per SM hide the
+// HBM latency by thread-level parallelism.  The kernel is bandwidth-bound; the MMA form is used
+// because it removes the FP64 issue/broadcast overhead a scalar formulation has, not
+// to chase flops.  cheb_step_fma is the scalar-FMA formulation of the same step (A/B reference).
+#include <algorithm>
+#include <cstring>
+
+#include "bdg_internal.h"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// ---- per-step reduction of the two dot products ---------------------------------------------
+// Every lane arrives with its partial sums for column `col` (valid iff col_ok and it is the
+// designated leader lane for that column inside the warp).  CTA partials go to global memory;
+// the last CTA of a panel to arrive adds them up in a fixed order (deterministic results) and
+// writes the step's dot products.
+template <int PW>
+__device__ __forceinline__ void finish_dots(double d0, double d1, int col, bool leader, int panel, int n_panels,
+                                            double *__restrict__ partials, unsigned *__restrict__ tickets,
+                                            double *__restrict__ dots_step) {
+    __shared__ double red[kWarps][2][8];
+    __shared__ double comb[16][16];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5;
+    if (leader) {
+        red[warp][0][col] = d0;
+        red[warp][1][col] = d1;
+    }
+    __syncthreads();
+    const int which = (threadIdx.x >> 3) & 1, c = threadIdx.x & 7;
+    if (threadIdx.x < 16 && c < PW) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][which][c];
+        partials[((size_t)(panel * gridDim.x + blockIdx.x) * 2 + which) * 8 + c] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // 16 (which, column) slots x 16 strided groups of CTAs, then a fixed-order combine.
+    const int slot = threadIdx.x & 15, group = threadIdx.x >> 4;
+    double s = 0.0;
+    for (unsigned b = group; b < gridDim.x; b += 16)
+        s += __ldcg(&partials[((size_t)(panel * gridDim.x + b) * 2) * 8 + slot]);
+    comb[group][slot] = s;
+    __syncthreads();
+    if (threadIdx.x < 16 && c < PW) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) t += comb[g][threadIdx.x];
+        dots_step[(size_t)which * n_panels * PW + panel * PW + c] = t;
+    }
+    if (threadIdx.x == 0) tickets[panel] = 0u;
+}
+
+// ---- the fused step: FP64 warp-MMA formulation --------------------------------------------------
+template <int PW, bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+cheb_step_dmma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+               const double2 *__restrict__ data, const double2 *__restrict__ x_cur, double2 *__restrict__ x_io,
+               int n_sites, int rows_per_cta, double alpha, double beta, double *__restrict__ partials,
+               unsigned *__restrict__ tickets, double *__restrict__ dots_step, int n_panels) {
+    constexpr int REC = PW * 4;  // complex elements per site record
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int panel = blockIdx.y;
+    const double2 *__restrict__ xc = x_cur + (size_t)panel * n_sites * REC;
+    double2 *__restrict__ xo = x_io + (size_t)panel * n_sites * REC;
+    const int row_begin = blockIdx.x * rows_per_cta;
+    const int row_end = min(n_sites, row_begin + rows_per_cta);
+
+    // A-operand role: lanes 0-15 feed rows 0-3 of [[Br,-Bi],[Bi,Br]], lanes 16-31 rows 4-7.
+    const int elem = lane & 15;
+    const bool hi = lane >= 16;
+    // B-operand role: lane l holds record element l = (column l/4, alpha l%4).
+    const bool x_lane = lane < REC;
+    // Output role after the re/im exchange: lane owns T_{n+1}[row][alpha=a][column=col].
+    const int a = (lane >> 2) & 3;
+    const int col = 2 * (lane & 3) + (lane >> 4);
+    const bool o_lane = col < PW;
+    const int o_elem = col * 4 + a;
+
+    double d0 = 0.0, d1 = 0.0;
+    for (int row = row_begin + warp; row < row_end; row += kWarps) {
+        const int p0 = indptr[row], p1 = indptr[row + 1];
+        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;  // two independent accumulation chains
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int cnt = min(32, p1 - pb);
+            const int jv = lane < cnt ? indices[pb + lane] : 0;
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                const int j = __shfl_sync(kFull, jv, t);
+                const double2 bv = __ldcs(data + (size_t)(pb + t) * 16 + elem);
+                double2 xv = make_double2(0.0, 0.0);
+                if (x_lane) xv = __ldg(xc + (size_t)j * REC + lane);
+                dmma_8x8x4(re0, re1, hi ? bv.y : bv.x, xv.x);   // [Br; Bi]  * Xr
+                dmma_8x8x4(im0, im1, hi ? bv.x : -bv.y, xv.y);  // [-Bi; Br] * Xi
+            }
+        }
+        const double c0 = re0 + im0, c1 = re1 + im1;
+        // Lanes < 16 hold Re(y) of (a, columns 2q, 2q+1), lanes >= 16 the matching Im(y):
+        // swap one value with the partner lane so each lane owns one complex element.
+        const double recv = __shfl_xor_sync(kFull, hi ? c0 : c1, 16);
+        const double yr = hi ? recv : c0;
+        const double yi = hi ? c1 : recv;
+        if (o_lane) {
+            const size_t off = (size_t)row * REC + o_elem;
+            const double2 tn = __ldg(xc + off);
+            double2 out;
+            if (FIRST) {
+                out = make_double2(alpha * yr, alpha * yi);
+            } else {
+                const double2 pv = xo[off];
+                out = make_double2(alpha * yr - beta * pv.x, alpha * yi - beta * pv.y);
+            }
+            xo[off] = out;
+            d0 += tn.x * tn.x + tn.y * tn.y;
+            d1 += out.x * tn.x + out.y * tn.y;
+        }
+    }
+    // lanes sharing a column differ in alpha (lane bits 2,3)
+    d0 += __shfl_xor_sync(kFull, d0, 4);
+    d1 += __shfl_xor_sync(kFull, d1, 4);
+    d0 += __shfl_xor_sync(kFull, d0, 8);
+    d1 += __shfl_xor_sync(kFull, d1, 8);
+    finish_dots<PW>(d0, d1, col, o_lane && a == 0, panel, n_panels, partials, tickets, dots_step);
+}
+
+// ---- the fused step: scalar FMA formulation (one thread per (site, column)) ----------------------
+template <int PW, bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+cheb_step_fma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+              const double2 *__restrict__ data, const double2 *__restrict__ x_cur, double2 *__restrict__ x_io,
+              int n_sites, int rows_per_cta, double alpha, double beta, double *__restrict__ partials,
+              unsigned *__restrict__ tickets, double *__restrict__ dots_step, int n_panels) {
+    constexpr int REC = PW * 4;
+    constexpr int ROWS_PER_WARP = 32 / PW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int panel = blockIdx.y;
+    const double2 *__restrict__ xc = x_cur + (size_t)panel * n_sites * REC;
+    double2 *__restrict__ xo = x_io + (size_t)panel * n_sites * REC;
+    const int row_begin = blockIdx.x * rows_per_cta;
+    const int row_end = min(n_sites, row_begin + rows_per_cta);
+    const int col = lane % PW, sub = lane / PW;
+
+    double d0 = 0.0, d1 = 0.0;
+    for (int base = row_begin + warp * ROWS_PER_WARP; base < row_end; base += kWarps * ROWS_PER_WARP) {
+        const int row = base + sub;
+        if (row >= row_end) continue;
+        double2 acc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = make_double2(0.0, 0.0);
+        for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+            const int j = indices[p];
+            const double2 *xb = xc + (size_t)j * REC + col * 4;
+            const double2 *blk = data + (size_t)p * 16;
+            double2 x[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[b] = __ldg(xb + b);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double2 m = __ldg(blk + r * 4 + b);
+                    acc[r].x += m.x * x[b].x - m.y * x[b].y;
+                    acc[r].y += m.x * x[b].y + m.y * x[b].x;
+                }
+            }
+        }
+        const size_t off = (size_t)row * REC + col * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double2 tn = __ldg(xc + off + r);
+            double2 out;
+            if (FIRST) {
+                out = make_double2(alpha * acc[r].x, alpha * acc[r].y);
+            } else {
+                const double2 pv = xo[off + r];
+                out = make_double2(alpha * acc[r].x - beta * pv.x, alpha * acc[r].y - beta * pv.y);
+            }
+            xo[off + r] = out;
+            d0 += tn.x * tn.x + tn.y * tn.y;
+            d1 += out.x * tn.x + out.y * tn.y;
+        }
+    }
+#pragma unroll
+    for (int d = PW; d < 32; d <<= 1) {
+        d0 += __shfl_xor_sync(kFull, d0, d);
+        d1 += __shfl_xor_sync(kFull, d1, d);
+    }
+    finish_dots<PW>(d0, d1, col, sub == 0, panel, n_panels, partials, tickets, dots_step);
+}
+
+// ---- start vectors ----------------------------------------------------------------------------
+// One thread per complex element of the padded vector set; columns >= n_cols are zero.
+__global__ void __launch_bounds__(kThreads)
+init_rademacher(double2 *__restrict__ x, int64_t n_elems, int n_sites, int pw, int n_cols, uint64_t seed,
+                int64_t col_offset) {
+    int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n_elems) return;
+    const int alpha = (int)(t & 3);
+    const int c = (int)((t >> 2) % pw);
+    const int64_t rec = (t >> 2) / pw;
+    const int site = (int)(rec % n_sites);
+    const int panel = (int)(rec / n_sites);
+    const int colg = panel * pw + c;
+    double v = 0.0;
+    if (colg < n_cols) {
+        const uint64_t G = 0x9E3779B97F4A7C15ull;
+        const uint64_t hc = mix64(seed + G * ((uint64_t)(col_offset + colg) + 1ull));
+        const uint64_t h = mix64(hc + G * ((uint64_t)(4 * (int64_t)site + alpha) + 1ull));
+        v = (h >> 63) ? -1.0 : 1.0;
+    }
+    x[t] = make_double2(v, 0.0);
+}
+
+__global__ void init_probes(double2 *__restrict__ x, int n_sites, int pw, int n_cols,
+                            const int64_t *__restrict__ probe_rows) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const int64_t r = probe_rows[c];
+    const int64_t site = r >> 2;
+    const int alpha = (int)(r & 3);
+    const int panel = c / pw, cl = c % pw;
+    x[(((size_t)panel * n_sites + site) * pw + cl) * 4 + alpha] = make_double2(1.0, 0.0);
+}
+
+// mu[n][c] from the per-step dot products: step s gave d0 = <T_s,T_s> (s = 0: <T_0,T_0>) and
+// d1 = <T_{s+1},T_s>;  mu_{2s} = 2 d0 - mu_0, mu_{2s+1} = 2 d1 - mu_1 for s >= 1.
+__global__ void __launch_bounds__(kThreads)
+moments_from_dots(const double *__restrict__ dots, int n_moments, int n_cols, int stride /* n_panels*PW */,
+                  int reduce, double *__restrict__ mu) {
+    int t = blockIdx.x * kThreads + threadIdx.x;
+    const int n_out = reduce ? 1 : n_cols;
+    if (t >= n_moments * n_out) return;
+    const int n = t / n_out, c_first = reduce ? 0 : t % n_out, c_last = reduce ? n_cols : c_first + 1;
+    const int s = n >> 1, which = n & 1;
+    double sum = 0.0;
+    for (int c = c_first; c < c_last; ++c) {
+        const double d = dots[((size_t)s * 2 + which) * stride + c];
+        sum += s == 0 ? d : 2.0 * d - dots[(size_t)which * stride + c];
+    }
+    mu[t] = sum;
+}
+
+// [panel][site][col][alpha] -> row-major [4N][n_cols]
+__global__ void __launch_bounds__(kThreads)
+unpack_vectors(const double2 *__restrict__ x, int n_sites, int pw, int n_cols, double2 *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= (int64_t)n_sites * 4 * n_cols) return;
+    const int c = (int)(t % n_cols);
+    const int64_t r = t / n_cols;
+    const int64_t site = r >> 2;
+    const int alpha = (int)(r & 3);
+    out[t] = x[(((size_t)(c / pw) * n_sites + site) * pw + (c % pw)) * 4 + alpha];
+}
+
+using StepKernel = void (*)(const int32_t *, const int32_t *, const double2 *, const double2 *, double2 *, int, int,
+                            double, double, double *, unsigned *, double *, int);
+
+template <int PW> StepKernel pick_pw(int kernel, bool first) {
+    if (kernel == BDG_KERNEL_FMA) return first ? cheb_step_fma<PW, true> : cheb_step_fma<PW, false>;
+    return first ? cheb_step_dmma<PW, true> : cheb_step_dmma<PW, false>;
+}
+
+StepKernel pick_kernel(int kernel, int pw, bool first) {
+    switch (pw) {
+        case 1: return pick_pw<1>(kernel, first);
+        case 2: return pick_pw<2>(kernel, first);
+        case 4: return pick_pw<4>(kernel, first);
+        default: return pick_pw<8>(kernel, first);
+    }
+}
+
+int launch_step(bdg_system *sys, bool first) {
+    ChebState &st = sys->cheb;
+    const BsrDev &m = sys->packed;
+    const int slot = first ? 0 : st.steps_done + 1;
+    const int stride = st.n_panels * st.panel_width;
+    double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
+    const double2 *x_cur = st.vec[st.cur].as<double2>();
+    double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
+    const int rows_per_cta = (int)ceil_div(m.n_sites, st.grid_x);
+    StepKernel k = pick_kernel(st.kernel, st.panel_width, first);
+    dim3 grid((unsigned)st.grid_x, (unsigned)st.n_panels);
+    k<<<grid, kThreads, 0, sys->stream>>>(m.indptr.as<int32_t>(), m.indices.as<int32_t>(), m.data.as<double2>(), x_cur,
+                                          x_io, (int)m.n_sites, rows_per_cta, (first ? 1.0 : 2.0) / st.scale,
+                                          first ? 0.0 : 1.0, st.partials.as<double>(), st.tickets.as<unsigned>(),
+                                          dots_step, st.n_panels);
+    BDG_CUDA(cudaGetLastError());
+    st.cur ^= 1;
+    st.launches += 1;
+    return BDG_OK;
+}
+
+int ensure_dot_capacity(bdg_system *sys, int steps_total) {
+    ChebState &st = sys->cheb;
+    if (steps_total + 1 <= st.dot_capacity) return BDG_OK;
+    const int stride = st.n_panels * st.panel_width;
+    int cap = std::max(steps_total + 1, std::max(1024, st.dot_capacity * 2));
+    DevBuf grown;
+    BDG_TRY(dev_alloc(sys, grown, (size_t)cap * 2 * stride * sizeof(double)));
+    if (st.dots.ptr && st.dot_capacity > 0) {
+        BDG_CUDA(cudaMemcpyAsync(grown.ptr, st.dots.ptr, (size_t)st.dot_capacity * 2 * stride * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, sys->stream));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    }
+    dev_free(sys, st.dots);
+    st.dots = grown;
+    st.dot_capacity = cap;
+    return BDG_OK;
+}
+
+}  // namespace
+
+void cheb_deactivate(bdg_system *sys) { sys->cheb.active = false; }
+
+void cheb_release(bdg_system *sys) {
+    ChebState &st = sys->cheb;
+    cudaStreamSynchronize(sys->stream);
+    dev_free(sys, st.vec[0]);
+    dev_free(sys, st.vec[1]);
+    dev_free(sys, st.dots);
+    dev_free(sys, st.partials);
+    dev_free(sys, st.tickets);
+    dev_free(sys, st.mu_tmp);
+    const int64_t launches = st.launches;
+    st = ChebState();
+    st.launches = launches;
+}
+
+#define BDG_ENTER(sys)                                                 \
+    BDG_REQUIRE((sys) != nullptr, "null handle");                      \
+    BDG_CUDA(cudaSetDevice((sys)->device))
+
+extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_rows, uint64_t seed,
+                              int64_t col_offset, double scale, int kernel) {
+    BDG_ENTER(sys);
+    BDG_REQUIRE(kind == BDG_X0_PROBE || kind == BDG_X0_RADEMACHER, "unknown start-vector kind %d", kind);
+    BDG_REQUIRE(n_cols >= 1, "need at least one column");
+    BDG_REQUIRE(scale > 0.0, "scale must be positive");
+    BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
+    BDG_REQUIRE(kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_DMMA || kernel == BDG_KERNEL_FMA, "unknown kernel %d", kernel);
+    BDG_TRY(build_packed(sys));
+    const BsrDev &m = sys->packed;
+    const int n = (int)m.n_sites;
+    if (kind == BDG_X0_PROBE)
+        for (int c = 0; c < n_cols; ++c)
+            BDG_REQUIRE(probe_rows[c] >= 0 && probe_rows[c] < 4 * (int64_t)n, "probe row %lld out of range", (long long)probe_rows[c]);
+
+    // Buffers of a previous recursion are kept and reused when large enough (parameter sweeps).
+    ChebState &st = sys->cheb;
+    st.active = false;
+    st.kernel = kernel == BDG_KERNEL_AUTO ? BDG_KERNEL_DMMA : kernel;
+    st.n_cols = n_cols;
+    st.panel_width = n_cols >= 5 ? 8 : (n_cols >= 3 ? 4 : n_cols);
+    st.n_panels = (int)ceil_div(n_cols, st.panel_width);
+    st.scale = scale;
+    st.steps_done = 0;
+    st.cur = 0;
+    st.dot_capacity = (int)(st.dots.bytes / ((size_t)2 * st.n_panels * st.panel_width * sizeof(double)));
+
+    // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
+    // walks one contiguous range of block rows (neighbouring rows share their X records in L1).
+    int per_sm = 1;
+    BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(st.kernel, st.panel_width, false), kThreads, 0));
+    per_sm = std::max(per_sm, 1);
+    const int64_t target = (int64_t)sys->sm_count * per_sm;
+    int64_t gx = std::max<int64_t>(1, target / st.n_panels);
+    const int rows_per_warp_pass = st.kernel == BDG_KERNEL_FMA ? kWarps * (32 / st.panel_width) : kWarps;
+    gx = std::min<int64_t>(gx, ceil_div(n, rows_per_warp_pass));
+    st.grid_x = (int)gx;
+
+    const size_t vec_elems = (size_t)st.n_panels * n * st.panel_width * 4;
+    BDG_TRY(dev_alloc(sys, st.vec[0], vec_elems * sizeof(double2)));
+    BDG_TRY(dev_alloc(sys, st.vec[1], vec_elems * sizeof(double2)));
+    BDG_TRY(dev_alloc(sys, st.partials, (size_t)st.n_panels * st.grid_x * 16 * sizeof(double)));
+    BDG_TRY(dev_alloc(sys, st.tickets, (size_t)st.n_panels * sizeof(unsigned)));
+    BDG_CUDA(cudaMemsetAsync(st.tickets.ptr, 0, (size_t)st.n_panels * sizeof(unsigned), sys->stream));
+    BDG_TRY(ensure_dot_capacity(sys, 1024));
+    st.active = true;
+
+    double2 *x0 = st.vec[0].as<double2>();
+    if (kind == BDG_X0_RADEMACHER) {
+        init_rademacher<<<(unsigned)ceil_div((int64_t)vec_elems, kThreads), kThreads, 0, sys->stream>>>(
+            x0, (int64_t)vec_elems, n, st.panel_width, n_cols, seed, col_offset);
+    } else {
+        BDG_CUDA(cudaMemsetAsync(x0, 0, vec_elems * sizeof(double2), sys->stream));
+        BDG_TRY(dev_alloc(sys, st.mu_tmp, (size_t)n_cols * sizeof(int64_t)));
+        BDG_CUDA(cudaMemcpyAsync(st.mu_tmp.ptr, probe_rows, (size_t)n_cols * sizeof(int64_t), cudaMemcpyHostToDevice, sys->stream));
+        init_probes<<<(unsigned)ceil_div(n_cols, 128), 128, 0, sys->stream>>>(x0, n, st.panel_width, n_cols,
+                                                                            st.mu_tmp.as<int64_t>());
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));  // probe_rows is borrowed only for this call
+    }
+    BDG_CUDA(cudaGetLastError());
+    st.launches += 1;
+    // T_1 = H~ T_0 (written into vec[1]); afterwards cur = 1 holds T_1, vec[0] holds T_0.
+    BDG_TRY(launch_step(sys, true));
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
+    BDG_ENTER(sys);
+    ChebState &st = sys->cheb;
+    BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
+    BDG_REQUIRE(n_steps >= 0, "negative step count");
+    BDG_TRY(ensure_dot_capacity(sys, st.steps_done + n_steps));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (elapsed_ms) {
+        BDG_CUDA(cudaEventCreate(&e0));
+        BDG_CUDA(cudaEventCreate(&e1));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+        BDG_CUDA(cudaEventRecord(e0, sys->stream));
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        BDG_TRY(launch_step(sys, false));
+        st.steps_done += 1;
+    }
+    if (elapsed_ms) {
+        BDG_CUDA(cudaEventRecord(e1, sys->stream));
+        BDG_CUDA(cudaEventSynchronize(e1));
+        BDG_CUDA(cudaEventElapsedTime(elapsed_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_available(bdg_t *sys, int32_t *n_moments) {
+    BDG_REQUIRE(sys && n_moments, "null argument");
+    *n_moments = sys->cheb.active ? 2 * (sys->cheb.steps_done + 1) : 0;
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_moments_read(bdg_t *sys, int32_t n_moments, int reduce, double *mu, int mu_on_device) {
+    BDG_ENTER(sys);
+    ChebState &st = sys->cheb;
+    BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
+    BDG_REQUIRE(mu != nullptr, "null output");
+    BDG_REQUIRE(n_moments >= 1 && n_moments <= 2 * (st.steps_done + 1), "only %d moments available, %d requested",
+                2 * (st.steps_done + 1), n_moments);
+    BDG_REQUIRE(reduce == BDG_MU_PER_COLUMN || reduce == BDG_MU_SUM, "unknown reduce mode");
+    const int n_out = reduce ? 1 : st.n_cols;
+    const size_t count = (size_t)n_moments * n_out;
+    double *dst = mu;
+    if (!mu_on_device) {
+        BDG_TRY(dev_alloc(sys, st.mu_tmp, count * sizeof(double)));
+        dst = st.mu_tmp.as<double>();
+    }
+    moments_from_dots<<<(unsigned)ceil_div((int64_t)count, kThreads), kThreads, 0, sys->stream>>>(
+        st.dots.as<double>(), n_moments, st.n_cols, st.n_panels * st.panel_width, reduce, dst);
+    BDG_CUDA(cudaGetLastError());
+    st.launches += 1;
+    if (!mu_on_device) {
+        BDG_CUDA(cudaMemcpyAsync(mu, dst, count * sizeof(double), cudaMemcpyDeviceToHost, sys->stream));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    }
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_moments(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_rows, uint64_t seed,
+                                int64_t col_offset, double scale, int32_t n_moments, int reduce, double *mu,
+                                int mu_on_device) {
+    BDG_REQUIRE(n_moments >= 1, "need at least one moment");
+    BDG_TRY(bdg_cheb_begin(sys, kind, n_cols, probe_rows, seed, col_offset, scale, BDG_KERNEL_AUTO));
+    BDG_TRY(bdg_cheb_steps(sys, (n_moments + 1) / 2 - 1, nullptr));
+    return bdg_cheb_moments_read(sys, n_moments, reduce, mu, mu_on_device);
+}
+
+extern "C" int bdg_cheb_vectors(bdg_t *sys, int which, double *out) {
+    BDG_ENTER(sys);
+    ChebState &st = sys->cheb;
+    BDG_REQUIRE(st.active && out, "no active recursion or null output");
+    BDG_REQUIRE(which == 0 || which == 1, "which must be 0 (T_n) or 1 (T_{n-1})");
+    const BsrDev &m = sys->packed;
+    const size_t count = (size_t)m.n_sites * 4 * st.n_cols;
+    DevBuf tmp;
+    BDG_TRY(dev_alloc(sys, tmp, count * sizeof(double2)));
+    unpack_vectors<<<(unsigned)ceil_div((int64_t)count, kThreads), kThreads, 0, sys->stream>>>(
+        st.vec[st.cur ^ which].as<double2>(), (int)m.n_sites, st.panel_width, st.n_cols, tmp.as<double2>());
+    cudaError_t err = cudaMemcpyAsync(out, tmp.ptr, count * sizeof(double2), cudaMemcpyDeviceToHost, sys->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(sys->stream);
+    dev_free(sys, tmp);
+    BDG_CUDA(err);
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_info(bdg_t *sys, int64_t *n_blocks, int64_t *bytes_per_step, int32_t *panel_width,
+                             int32_t *n_panels, int64_t *launches) {
+    BDG_ENTER(sys);
+    const ChebState &st = sys->cheb;
+    BDG_TRY(build_packed(sys));
+    const BsrDev &m = sys->packed;
+    if (n_blocks) *n_blocks = m.n_blocks;
+    if (bytes_per_step)
+        *bytes_per_step = 260 * m.n_blocks + 4 * (m.n_sites + 1) + (int64_t)192 * m.n_sites * st.n_cols;
+    if (panel_width) *panel_width = st.panel_width;
+    if (n_panels) *n_panels = st.n_panels;
+    if (launches) *launches = st.launches;
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_end(bdg_t *sys) {
+    BDG_ENTER(sys);
+    cheb_release(sys);
+    return BDG_OK;
+}

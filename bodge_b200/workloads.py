@@ -1,0 +1,111 @@
+"""Synthetic workloads of the benchmark configs as *packed arrays* (SURVEY 8d).
+
+Million-site systems cannot afford a Python loop per site (the reference's dict API costs
+~34 µs per site in user code alone), so the bench and the full-size tests generate the very
+same Hamiltonian terms vectorised and feed them to ``Hamiltonian.fill``.  Every builder
+returns ``(h_i, h_j, h_val, p_i, p_j, p_val)``: flat site indices (int32) and ``[n, 2, 2]``
+complex128 values of the ``H[i, j]`` and ``Δ[i, j]`` entries, i.e. exactly what the dict API
+would have collected.  ``tests/`` checks them against the dict-API builders on small lattices.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .common import jσ2, σ0, σ1, σ2, σ3
+from .lattice import CubicLattice
+
+
+def _bonds(lattice: CubicLattice, axis: int):
+    """Directed bonds along ``axis``: (i -> j) followed by (j -> i)."""
+    i, j = lattice.bonds_array(axis)
+    return np.concatenate([i, j]), np.concatenate([j, i])
+
+
+def _tile(mat, n):
+    return np.broadcast_to(np.asarray(mat, dtype=np.complex128), (n, 2, 2)).copy()
+
+
+def _finish(h_i, h_j, h_val, p_i, p_j, p_val):
+    cat = np.concatenate
+    return (cat(h_i).astype(np.int32), cat(h_j).astype(np.int32), cat(h_val),
+            cat(p_i).astype(np.int32), cat(p_j).astype(np.int32), cat(p_val))
+
+
+def readme_swave(shape, mu=-3.0, m=0.05, ds=0.10, t=1.0):
+    """README model (reference README.md:73-86): C1, C2 and (m = 0, 3-D) C4."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    sites = np.arange(n, dtype=np.int64)
+    h_i, h_j, h_val = [sites], [sites], [_tile(-mu * σ0 - m * σ3, n)]
+    p_i, p_j, p_val = [sites], [sites], [_tile(-ds * jσ2, n)]
+    for axis in (2, 1, 0):
+        i, j = _bonds(lat, axis)
+        h_i.append(i)
+        h_j.append(j)
+        h_val.append(_tile(-t * σ0, len(i)))
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
+def swave_3d(shape, mu=-3.0, ds=0.1, t=1.0):
+    """C4: README on-site terms without spin splitting on a 3-D lattice."""
+    return readme_swave(shape, mu=mu, m=0.0, ds=ds, t=t)
+
+
+def dwave_rashba(shape, mu=-0.5, alpha=0.2, dd=0.1, t=1.0):
+    """C3: d_{x²-y²} pairing on the bonds + Rashba spin-orbit hopping."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    sites = np.arange(n, dtype=np.int64)
+    h_i, h_j, h_val = [sites], [sites], [_tile(-mu * σ0, n)]
+    p_i, p_j, p_val = [], [], []
+    for axis in (2, 1, 0):
+        lo, hi = lat.bonds_array(axis)
+        for i, j, sign in ((lo, hi, +1), (hi, lo, -1)):
+            delta = np.zeros(3)
+            delta[axis] = sign
+            hop = -t * σ0 + 1j * alpha * (delta[1] * σ1 - delta[0] * σ2)
+            weight = (delta[0] ** 2 - delta[1] ** 2) / (np.sum(delta**2) + 1e-16)
+            h_i.append(i)
+            h_j.append(j)
+            h_val.append(_tile(hop, len(i)))
+            p_i.append(i)
+            p_j.append(j)
+            p_val.append(_tile(-dd * (weight * jσ2), len(i)))
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
+def junction(shape, mu=-3.0, d0=0.2, phi=np.pi / 2, m=0.3, t=1.0):
+    """C5: superconductor / altermagnet / superconductor Josephson junction along x."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    Lx, Ly, Lz = shape
+    x1, x2 = Lx // 3, Lx - Lx // 3
+    sites = np.arange(n, dtype=np.int64)
+    x_of = sites // (Ly * Lz)
+    h_i, h_j, h_val = [sites], [sites], [_tile(-mu * σ0, n)]
+    left, right = sites[x_of < x1], sites[x_of >= x2]
+    p_i, p_j = [left, right], [left, right]
+    p_val = [_tile(-d0 * jσ2 * np.exp(-0.5j * phi), len(left)), _tile(-d0 * jσ2 * np.exp(+0.5j * phi), len(right))]
+    for axis in (2, 1, 0):
+        i, j = _bonds(lat, axis)
+        xi, xj = i // (Ly * Lz), j // (Ly * Lz)
+        mid = (xi >= x1) & (xi < x2) & (xj >= x1) & (xj < x2)
+        vals = _tile(-t * σ0, len(i))
+        if axis == 0:
+            vals[mid] = -t * σ0 - m * σ3
+        elif axis == 1:
+            vals[mid] = -t * σ0 + m * σ3
+        h_i.append(i)
+        h_j.append(j)
+        h_val.append(vals)
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
+CONFIGS = {
+    "C1": dict(shape=(40, 40, 1), build=readme_swave, label="CubicLattice((40,40,1)) README s-wave"),
+    "C2": dict(shape=(100, 100, 1), build=readme_swave, label="CubicLattice((100,100,1)) README s-wave + spin splitting"),
+    "C3": dict(shape=(100, 100, 1), build=dwave_rashba, label="CubicLattice((100,100,1)) d-wave + Rashba SOC"),
+    "C4": dict(shape=(64, 64, 64), build=swave_3d, label="CubicLattice((64,64,64)) 3D s-wave"),
+    "C5": dict(shape=(1000, 1000, 1), build=junction, label="CubicLattice((1000,1000,1)) altermagnet/SC Josephson junction"),
+}

@@ -1,0 +1,138 @@
+/*
+ * bdg.h -- C ABI of libbdg: B200-native (sm_100a) BdG Hamiltonian assembly and
+ * Chebyshev/KPM expansion.  This is the drop-in boundary for the numerical hot path of
+ * jabirali/bodge v1.3.0; every entry point names the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C types only; all arrays are caller-owned and borrowed for the duration of a call;
+ *   - host pointers unless a parameter says "device";
+ *   - every function returns 0 on success or a BDG_E_* code; bdg_last_error() gives the text
+ *     of the last failure on the calling thread;
+ *   - one bdg_t owns all device memory of one Hamiltonian on one GPU and one CUDA stream
+ *     (its own by default, or a borrowed one via bdg_set_stream); not thread-safe per handle;
+ *   - complex numbers are interleaved (re, im) doubles = numpy complex128;
+ *   - site indices are the lattice's flat indices (bodge/lattice.py:101-108), scalar rows are
+ *     4*site + alpha with alpha in (e-up, e-down, h-up, h-down) (bodge README.md:110-115).
+ */
+#ifndef BDG_H
+#define BDG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDG_ABI_VERSION 1
+
+enum {
+    BDG_OK = 0,
+    BDG_E_INVALID = 1,       /* bad argument / bad state            -> ValueError / RuntimeError      */
+    BDG_E_CUDA = 2,          /* CUDA runtime failure                -> RuntimeError                   */
+    BDG_E_NOT_NEIGHBOUR = 3, /* (i,j) is not a block of the skeleton -> IndexError  (hamiltonian.py:170) */
+    BDG_E_NOT_HERMITIAN = 4, /* max|M - M^H| > tol                  -> RuntimeError (hamiltonian.py:122) */
+    BDG_E_OUT_OF_BOUNDS = 5, /* site index outside [0, N)           -> ValueError   (lattice.py:106)  */
+    BDG_E_NO_DEVICE = 6      /* no usable CUDA device               -> RuntimeError                   */
+};
+
+typedef struct bdg_system bdg_t;
+
+/* ---- housekeeping ------------------------------------------------------------------ */
+int bdg_abi_version(void);
+const char *bdg_last_error(void);
+int bdg_device_count(int *count);
+int bdg_destroy(bdg_t *sys);
+/* Borrow a CUDA stream (cudaStream_t / CUstream as void*); NULL restores the handle's own. */
+int bdg_set_stream(bdg_t *sys, void *stream);
+int bdg_sync(bdg_t *sys);
+/* Bytes of device memory currently owned by the handle. */
+int bdg_device_bytes(bdg_t *sys, int64_t *bytes);
+/* Page-locked host buffers for callers that want full-rate host<->device copies of the packed
+ * entry arrays (any host memory works; pageable memory is staged by the driver). */
+int bdg_pinned_alloc(int64_t bytes, void **out);
+int bdg_pinned_free(void *ptr);
+
+/* ---- skeleton: replaces Hamiltonian.__init__ (bodge/hamiltonian.py:25-67) ------------ */
+/* Periodic-stencil skeleton of CubicLattice((Lx,Ly,Lz)) built on the device: per-site sorted,
+ * de-duplicated neighbour lists in registers, warp-shuffle scan for indptr.  Equals what the
+ * reference obtains from lattice.sites() + bonds() + edges() through scipy coo->bsr. */
+int bdg_create_cubic(int device, int32_t Lx, int32_t Ly, int32_t Lz, bdg_t **out);
+/* Any Lattice subclass: pairs (i,j) as yielded by `for ri, rj in lattice` (flat indices).
+ * Both orientations are inserted, duplicates merged, rows sorted (bucket-by-row + per-row sort). */
+int bdg_create_generic(int device, int64_t n_sites, int64_t n_pairs, const int32_t *pair_i,
+                       const int32_t *pair_j, bdg_t **out);
+int bdg_skeleton_sizes(bdg_t *sys, int64_t *n_sites, int64_t *n_blocks);
+
+/* ---- block lookup: replaces Hamiltonian.index (bodge/hamiltonian.py:157-170) --------- */
+/* k[e] = position of block (i[e], j[e]) in the skeleton's data array.  BDG_E_NOT_NEIGHBOUR /
+ * BDG_E_OUT_OF_BOUNDS with *bad_entry = first offending e otherwise. */
+int bdg_lookup(bdg_t *sys, int64_t n, const int32_t *i, const int32_t *j, int64_t *k,
+               int64_t *bad_entry);
+
+/* ---- scatter: replaces Hamiltonian.__exit__ (bodge/hamiltonian.py:91-126) ------------ */
+/* h_val / p_val: [n,2,2] complex128.  For every hopping entry  blk(i,j)[0:2,0:2] = H,
+ * blk(i,j)[2:4,2:4] = -conj(H); for every pairing entry  blk(i,j)[0:2,2:4] = D,
+ * blk(j,i)[2:4,0:2] = D^dagger.  Keys must be unique within each list (they come from a dict).
+ * As in the reference, entries before the first failing lookup are applied and the rest are not
+ * (hopping entries first, then pairing), and the Hermitian check runs last:
+ * *max_dev = max|M - M^H|; returns BDG_E_NOT_HERMITIAN when it exceeds herm_tol (state stays
+ * modified, like the reference).  herm_tol < 0 skips the check. */
+int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const int32_t *h_j,
+                const double *h_val, int64_t n_pair, const int32_t *p_i, const int32_t *p_j,
+                const double *p_val, double herm_tol, double *max_dev, int64_t *bad_entry);
+/* Set every stored value back to zero (fresh skeleton). */
+int bdg_clear(bdg_t *sys);
+
+/* ---- export: replaces Hamiltonian.matrix("bsr") / ._matrix (bodge/hamiltonian.py:128-143) */
+/* Two-phase: call with indptr = indices = data = NULL to get *n_blocks, then with buffers
+ * indptr[N+1] int32, indices[nb] int32, data[nb*32] double.  eliminate_zeros != 0 drops every
+ * block whose 16 entries all compare == 0 (scipy bsr eliminate_zeros), else the full skeleton. */
+int bdg_export_bsr(bdg_t *sys, int eliminate_zeros, int64_t *n_blocks, int32_t *indptr,
+                   int32_t *indices, double *data);
+/* Overwrite all stored values from a host array laid out like the skeleton's data (inverse of
+ * export with eliminate_zeros = 0; used for `system._data[...] = ...` style direct edits). */
+int bdg_import_data(bdg_t *sys, const double *data);
+
+/* ---- spectral bound -------------------------------------------------------------------- */
+/* *norm = max absolute row sum of the 4N x 4N matrix (>= spectral radius). */
+int bdg_norm_inf(bdg_t *sys, double *norm);
+
+/* ---- Chebyshev / KPM engine (no reference code; arithmetic = scipy bsr_matvecs on
+ *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
+enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
+enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
+enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2 };
+
+/* Start a recursion on n_cols start vectors resident on this GPU.
+ *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)
+ *   kind = BDG_X0_RADEMACHER: column c = +-1 vector hashed from (seed, row, col_offset + c)
+ * scale = a  (H~ = H / a must have its spectrum inside [-1, 1]).
+ * Builds T_0 = X0 and T_1 = H~ T_0 and the first two dot products. */
+int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_rows, uint64_t seed,
+                   int64_t col_offset, double scale, int kernel);
+/* Enqueue n_steps fused steps T_{n+1} = 2 H~ T_n - T_{n-1} (+ <T_n,T_n>, <T_{n+1},T_n>).
+ * elapsed_ms != NULL: bracket the steps with CUDA events on the handle's stream, synchronise,
+ * and return the device time. */
+int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms);
+/* Moments available so far: 2 * (steps + 1). */
+int bdg_cheb_available(bdg_t *sys, int32_t *n_moments);
+/* mu[n * n_out + c], n < n_moments; n_out = n_cols (BDG_MU_PER_COLUMN) or 1 (BDG_MU_SUM, summed
+ * over this GPU's columns).  mu_on_device != 0: mu is a device pointer (e.g. for an NCCL reduce). */
+int bdg_cheb_moments_read(bdg_t *sys, int32_t n_moments, int reduce, double *mu, int mu_on_device);
+/* Convenience: begin + ceil(n_moments/2)-1 steps + read. */
+int bdg_cheb_moments(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_rows,
+                     uint64_t seed, int64_t col_offset, double scale, int32_t n_moments,
+                     int reduce, double *mu, int mu_on_device);
+/* Copy the current T_n ([4N, n_cols] row-major complex128) to the host (testing / debugging). */
+int bdg_cheb_vectors(bdg_t *sys, int which /*0 = T_n, 1 = T_{n-1}*/, double *out);
+/* Algorithmic bytes of one step at the current configuration (SURVEY 8d formula) and the
+ * number of blocks after eliminate_zeros. */
+int bdg_cheb_info(bdg_t *sys, int64_t *n_blocks, int64_t *bytes_per_step, int32_t *panel_width,
+                  int32_t *n_panels, int64_t *launches);
+int bdg_cheb_end(bdg_t *sys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDG_H */
