@@ -1,0 +1,217 @@
+"""Parity of the CUDA Chebyshev/KPM engine with the oracle (scipy bsr_matvecs recursion on the
+same matrix) and, through free_energy / ldos, with the reference's own observables.
+
+Tolerances (BASELINE.json north_star): moments and free energy within 1e-10 relative.
+Moments are compared norm-wise (max|Δμ| / max|μ|): high orders pass through zero.
+"""
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import bdg_oracle as orc
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def scipy_of(system):
+    return system.matrix("bsr")
+
+
+@pytest.fixture(scope="module")
+def random_system(gpu_api):
+    return cases.random_periodic(gpu_api, (3, 5, 7), seed=11)
+
+
+@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+@pytest.mark.parametrize("n_cols", [1, 2, 3, 4, 5, 8, 12, 19])
+def test_random_column_moments(random_system, kernel, n_cols):
+    system = random_system
+    H = scipy_of(system)
+    scale = system.spectral_bound()
+    x0 = orc.rademacher(99, H.shape[0], np.arange(n_cols))
+    want = orc.cheb_moments(H, x0, 64, scale)
+    got = system.chebyshev_moments(64, vectors=n_cols, seed=99, scale=scale, kernel=kernel)
+    assert got.shape == want.shape
+    assert rel_err(got, want) <= TOL
+    summed = system.chebyshev_moments(64, vectors=n_cols, seed=99, scale=scale, kernel=kernel, summed=True)
+    assert rel_err(summed, want.sum(axis=1)) <= TOL
+
+
+@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+def test_probe_moments_match_fixture(gpu_api, observables, kernel):
+    """Fixture = scipy recursion on the REFERENCE's own matrix("bsr")."""
+    builders = {"readme_12_12_1": lambda: cases.readme_swave(gpu_api, (12, 12, 1)),
+                "random_3_5_7": lambda: cases.random_periodic(gpu_api, (3, 5, 7), seed=11),
+                "dwave_9_8_1": lambda: cases.dwave_rashba(gpu_api, (9, 8, 1))}
+    for tag, make in builders.items():
+        system = make()
+        want = observables[f"mu_{tag}"]
+        scale, site = float(observables[f"mu_{tag}_scale"]), int(observables[f"mu_{tag}_site"])
+        assert abs(system.spectral_bound() - scale) <= 1e-12 * scale
+        probes = system.chebyshev_moments(want.shape[0], rows=[4 * site + a for a in range(4)], scale=scale, kernel=kernel)
+        random = system.chebyshev_moments(want.shape[0], vectors=4, seed=1234, scale=scale, kernel=kernel)
+        assert rel_err(probes, want[:, :4]) <= TOL
+        assert rel_err(random, want[:, 4:]) <= TOL
+
+
+@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+def test_recursion_vectors(random_system, kernel):
+    """The vectors themselves after a few steps: T_n and T_{n-1} against the scipy recursion."""
+    system = random_system
+    H = scipy_of(system)
+    scale = system.spectral_bound()
+    n_cols, steps = 5, 6
+    x0 = orc.rademacher(5, H.shape[0], np.arange(n_cols) + 3)
+    t_prev, t_cur = x0, (H / scale) @ x0
+    for _ in range(steps):
+        t_prev, t_cur = t_cur, orc.cheb_step(H / scale, t_cur, t_prev)
+    sysn = system._sys
+    sysn.cheb_begin(n_random=n_cols, seed=5, col_offset=3, scale=scale, kernel=kernel)
+    sysn.cheb_steps(steps)
+    assert np.max(np.abs(sysn.cheb_vectors(n_cols, 0) - t_cur)) <= 1e-12 * np.max(np.abs(t_cur))
+    assert np.max(np.abs(sysn.cheb_vectors(n_cols, 1) - t_prev)) <= 1e-12 * np.max(np.abs(t_prev))
+    sysn.cheb_end()
+
+
+def test_start_vectors_are_the_oracles(random_system):
+    sysn = random_system._sys
+    n_rows = random_system.shape[0]
+    sysn.cheb_begin(n_random=11, seed=42, col_offset=7, scale=50.0)
+    assert np.array_equal(sysn.cheb_vectors(11, 1), orc.rademacher(42, n_rows, np.arange(11) + 7))
+    rows = [0, 5, n_rows - 1, 17, 17]
+    sysn.cheb_begin(probe_rows=rows, scale=50.0)
+    assert np.array_equal(sysn.cheb_vectors(5, 1), orc.probes(n_rows, rows))
+    sysn.cheb_end()
+
+
+def test_moment_properties_and_determinism(random_system):
+    system = random_system
+    rows = np.arange(0, system.shape[0], 13)
+    a = system.chebyshev_moments(200, rows=rows)
+    b = system.chebyshev_moments(200, rows=rows)
+    assert np.array_equal(a, b)                       # fixed-order reductions: bitwise repeatable
+    assert np.array_equal(a[0], np.ones(len(rows)))   # <e|e> = 1
+    assert np.max(np.abs(a)) <= 1 + 1e-12             # |<x|T_n|x>| <= <x|x>
+    fma = system.chebyshev_moments(200, rows=rows, kernel="fma")
+    assert rel_err(fma, a) <= 1e-12
+    # batching the columns must not change anything
+    c = system.chebyshev_moments(200, rows=rows, batch=8)
+    assert np.array_equal(a, c)
+    # odd number of moments
+    d = system.chebyshev_moments(7, rows=rows[:3])
+    assert np.array_equal(d, a[:7, :3])
+
+
+@pytest.mark.parametrize("tag", ["snf_10_7_3", "readme_12_12_1", "junction_30_10_1", "dwave_9_8_1"])
+def test_free_energy_matches_reference(gpu_api, observables, tag):
+    """free_energy(T, cuda=True) (KPM, exact trace) vs the reference's dense eigvalsh values."""
+    from test_oracle import SMALL
+
+    system = SMALL[tag](gpu_api)
+    for T, F_ref in zip(observables["temps"], observables[f"F_{tag}"]):
+        if T >= 0.05:
+            F = system.free_energy(float(T), cuda=True)
+            assert abs(F - F_ref) <= TOL * abs(F_ref), (tag, T, F, F_ref)
+        elif T > 0:
+            F = system.free_energy(float(T), cuda=True, moments=4096)
+            assert abs(F - F_ref) <= 1e-6 * abs(F_ref)
+    F0 = system.free_energy(0.0, cuda=True, moments=2048)
+    assert abs(F0 - observables[f"F_{tag}"][0]) <= 1e-4 * abs(F0)   # kink at ε=0: algebraic convergence
+    # the reference's own CPU-vs-GPU test template (tests/test_hamiltonian.py:421-425)
+    for T in [0.1, 1.0]:
+        assert np.allclose(system.free_energy(T, cuda=False), system.free_energy(T, cuda=True))
+    with pytest.raises(Exception):
+        system.free_energy(-1.0, cuda=True)
+
+
+def test_free_energy_C1_exact_trace(gpu_api, observables):
+    """Config C1 (40x40): all 6400 unit columns, vs the reference's dense value at T = 0.1."""
+    system = cases.readme_swave(gpu_api, (40, 40, 1))
+    temps, F_ref = observables["temps"], observables["F_C1"]
+    F = system.free_energy(0.1, cuda=True)
+    assert abs(F - F_ref[list(temps).index(0.1)]) <= TOL * abs(F)
+    F = system.free_energy(1.0, cuda=True)
+    assert abs(F - F_ref[list(temps).index(1.0)]) <= TOL * abs(F)
+    # stochastic trace: unbiased estimate, error ~ 1/sqrt(R * 4N)
+    Fs = system.free_energy(0.1, cuda=True, vectors=64, seed=1234)
+    assert abs(Fs - F) <= 2e-3 * abs(F)
+
+
+@pytest.mark.parametrize("tag,site", [("readme_12_12_1", (6, 6, 0)), ("random_5_5_2", (2, 3, 1)), ("dwave_9_8_1", (4, 4, 0))])
+def test_ldos_matches_reference(gpu_api, observables, tag, site):
+    from test_oracle import SMALL
+
+    system = SMALL[tag](gpu_api)
+    got = system.ldos(site, observables["ldos_E"])
+    assert rel_err(got, observables[f"ldos_{tag}"]) <= TOL
+    got = system.ldos(site, list(observables["ldos_E"]), kernel="fma")
+    assert rel_err(got, observables[f"ldos_{tag}"]) <= TOL
+
+
+def test_ldos_positive_everywhere(gpu_api):
+    # reference tests/test_hamiltonian.py:467-500
+    system = cases.random_periodic(gpu_api, (5, 5, 2), seed=21)
+    sites = [(i, j, k) for i in range(5) for j in range(5) for k in range(2)]
+    rho = system.ldos_map(sites, [0.0, 0.01, 0.10, 0.50, 1.00, 2.00, 4.00])
+    assert rho.shape == (50, 7) and (rho >= 0).all()
+
+
+def test_magnetic_isotropy(gpu_api):
+    """Rotating a homogeneous exchange field changes neither F nor the LDOS (rtol 1e-10), the
+    reference's tests/test_physics.py:115-172 on the KPM path."""
+    api = gpu_api
+    lattice = api.CubicLattice((128, 1, 1))
+    system = api.Hamiltonian(lattice)
+    with system as (H, D):
+        for i in lattice.sites():
+            D[i, i] = -0.1 * api.jσ2
+        for i, j in lattice.bonds():
+            H[i, j] = -1.0 * api.σ0
+    T, i0, E0 = 0.05, (64, 0, 0), [0.0, 0.05]
+    F0 = system.free_energy(T, cuda=True, scale=2.4)
+    r0 = system.ldos(i0, E0, scale=2.4)[0]
+    rng = np.random.default_rng(4)
+    Fs, rs = [], []
+    for _ in range(4):
+        th, ph = 2 * np.pi * rng.random(2)
+        s = np.cos(th) * api.σ1 + np.sin(th) * np.cos(ph) * api.σ2 + np.sin(th) * np.sin(ph) * api.σ3
+        with system as (H, D):
+            for i in lattice.sites():
+                H[i, i] = -0.05 * s
+        Fs.append(system.free_energy(T, cuda=True, scale=2.4))
+        rs.append(system.ldos(i0, E0, scale=2.4)[0])
+    assert all(not np.allclose(F0, F, rtol=1e-10) for F in Fs)
+    assert all(not np.allclose(r0, r, rtol=1e-10) for r in rs)
+    assert all(np.allclose(a, b, rtol=1e-10) for a, b in zip(Fs[:-1], Fs[1:]))
+    assert all(np.allclose(a, b, rtol=1e-9) for a, b in zip(rs[:-1], rs[1:]))
+
+
+def test_full_size_chebyshev_properties(gpu_api):
+    """C5 (10^6 sites, k = 8): properties that hold independent of size."""
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    shape = (1000, 1000, 1)
+    system = b.Hamiltonian(b.CubicLattice(shape))
+    system.fill(*workloads.junction(shape))
+    mu = system.chebyshev_moments(32, vectors=8, seed=1234)
+    assert np.array_equal(mu[0], np.full(8, 4e6))            # <x|x> = 4N exactly for +-1 vectors
+    assert np.max(np.abs(mu)) <= 4e6 * (1 + 1e-12)
+    assert np.max(np.abs(mu[1::2])) < 4e6 * 0.01              # odd moments ~ Tr-odd ~ 0 (± spectrum)
+    fma = system.chebyshev_moments(32, vectors=8, seed=1234, kernel="fma")
+    assert rel_err(fma, mu) <= 1e-12
+    # column sharding: columns 4..7 computed alone (as another GPU would) are bit-identical
+    sysn = system._sys
+    sysn.cheb_begin(n_random=4, seed=1234, col_offset=4, scale=system.spectral_bound())
+    sysn.cheb_steps(15)
+    part = sysn.cheb_read(32, 4)
+    assert rel_err(part, mu[:, 4:]) <= 1e-13
+    # a small twin of the same model agrees with the oracle end to end
+    small = b.Hamiltonian(b.CubicLattice((30, 10, 1)))
+    small.fill(*workloads.junction((30, 10, 1)))
+    H = small.matrix("bsr")
+    want = orc.cheb_moments(H, orc.rademacher(1234, H.shape[0], np.arange(8)), 32, small.spectral_bound())
+    assert rel_err(small.chebyshev_moments(32, vectors=8, seed=1234), want) <= TOL
