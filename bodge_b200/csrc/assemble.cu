@@ -395,9 +395,12 @@ __global__ void __launch_bounds__(kThreads) hermitian_dev(int64_t n_blocks, cons
     double dev = 0.0;
     if (k < n_blocks) {
         const int el = (int)(t & 15), a = el >> 2, b = el & 3;
+        // The 16 threads of one block form a half-warp; shuffle inside that half only -- the other
+        // half may belong to a block past the end (odd block counts) and not be here at all.
+        const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
         int kt = 0;
         if (el == 0) kt = find_block(indptr, indices, indices[k], brow[k]);
-        kt = __shfl_sync(0xffffffffu, kt, (threadIdx.x & 31) & 16);
+        kt = __shfl_sync(half_mask, kt, (threadIdx.x & 31) & 16);
         const double2 v = data[k * 16 + el];
         if (kt < 0) {
             dev = hypot(v.x, v.y);  // no transposed partner stored: compare with zero
@@ -430,12 +433,15 @@ __global__ void __launch_bounds__(kThreads) flag_nonzero(int64_t n_blocks, const
 
 __global__ void __launch_bounds__(kThreads) row_kept_counts(int n_sites, const int32_t *__restrict__ indptr,
                                                             const int32_t *__restrict__ flags,
-                                                            int32_t *__restrict__ counts) {
+                                                            int32_t *__restrict__ counts, int32_t *max_count) {
     int row = blockIdx.x * kThreads + threadIdx.x;
-    if (row >= n_sites) return;
     int c = 0;
-    for (int p = indptr[row]; p < indptr[row + 1]; ++p) c += flags[p];
-    counts[row] = c;
+    if (row < n_sites) {
+        for (int p = indptr[row]; p < indptr[row + 1]; ++p) c += flags[p];
+        counts[row] = c;
+    }
+    c = __reduce_max_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(max_count, c);
 }
 
 __global__ void __launch_bounds__(kThreads) compact_blocks(int64_t n_blocks, const int32_t *__restrict__ flags,
@@ -779,6 +785,7 @@ extern "C" int bdg_import_data(bdg_t *sys, const double *data) {
     return BDG_OK;
 }
 
+static int fetch_scalars(bdg_system *sys);
 // Build sys->packed = skeleton minus all-zero blocks (device resident; also feeds the Chebyshev engine).
 int build_packed(bdg_system *sys) {
     if (sys->packed_valid) return BDG_OK;
@@ -794,12 +801,15 @@ int build_packed(bdg_system *sys) {
     BDG_TRY(dev_alloc(sys, p.indptr, (size_t)(n + 1) * sizeof(int32_t)));
     int32_t *pptr = p.indptr.as<int32_t>();
     flag_nonzero<<<grid_for(nb * 16), kThreads, 0, sys->stream>>>(nb, m.data.as<double2>(), flags);
-    row_kept_counts<<<grid_for(n), kThreads, 0, sys->stream>>>(n, m.indptr.as<int32_t>(), flags, pptr);
+    BDG_CUDA(cudaMemsetAsync(&d->flag, 0, sizeof(int32_t), sys->stream));
+    row_kept_counts<<<grid_for(n), kThreads, 0, sys->stream>>>(n, m.indptr.as<int32_t>(), flags, pptr, &d->flag);
     BDG_TRY(exclusive_scan_i32(sys, pptr, pptr, n, &d->total));
     BDG_CUDA(cudaMemcpyAsync(pptr + n, &d->total, sizeof(int32_t), cudaMemcpyDeviceToDevice, sys->stream));
     BDG_TRY(exclusive_scan_i32(sys, flags, pos, nb, nullptr));
     int32_t kept = 0;
-    BDG_TRY(read_total(sys, &kept));
+    BDG_TRY(fetch_scalars(sys));
+    kept = static_cast<Scalars *>(sys->host_scalars)->total;
+    sys->packed_max_row = static_cast<Scalars *>(sys->host_scalars)->flag;
     p.n_sites = n;
     p.n_blocks = kept;
     BDG_TRY(dev_alloc(sys, p.indices, (size_t)kept * sizeof(int32_t)));

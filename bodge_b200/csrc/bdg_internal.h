@@ -91,6 +91,7 @@ struct bdg_system {
     BsrDev skel;           // full skeleton, values as scattered so far
     BsrDev packed;         // after eliminate_zeros (built lazily)
     bool packed_valid = false;
+    int packed_max_row = 0;  // longest block row of `packed` (picks the kernel's unroll)
 
     DevBuf scratch_i32[4];  // reusable scratch (counts, scans, flags, positions)
     DevBuf stage[10];       // uploaded entry lists: {i, j, values, k1, k2} x {hopping, pairing}

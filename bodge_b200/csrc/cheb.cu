@@ -28,14 +28,34 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;  // 128-thread CTAs: finer occupancy granularity at ~96 registers/thread
 constexpr int kThreads = kWarps * 32;
+constexpr int kGroups = kThreads / 16;  // strided CTA groups in the last-CTA reduction
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// 128-bit global loads as volatile asm: together with the (volatile) MMAs this pins the program
+// order "all loads of a row, then all MMAs", which the compiler otherwise interleaves to save
+// registers -- turning one HBM round trip per row into two or three.
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {  // read-once data (matrix blocks)
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_reuse(const double2 *p) {  // vector records (re-read by neighbours)
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_plain(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -54,7 +74,7 @@ __device__ __forceinline__ void finish_dots(double d0, double d1, int col, bool 
                                             double *__restrict__ partials, unsigned *__restrict__ tickets,
                                             double *__restrict__ dots_step) {
     __shared__ double red[kWarps][2][8];
-    __shared__ double comb[16][16];
+    __shared__ double comb[kGroups][16];
     __shared__ bool is_last;
     const int warp = threadIdx.x >> 5;
     if (leader) {
@@ -75,25 +95,34 @@ __device__ __forceinline__ void finish_dots(double d0, double d1, int col, bool 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // 16 (which, column) slots x 16 strided groups of CTAs, then a fixed-order combine.
+    // 16 (which, column) slots x kGroups strided groups of CTAs, then a fixed-order combine.
     const int slot = threadIdx.x & 15, group = threadIdx.x >> 4;
     double s = 0.0;
-    for (unsigned b = group; b < gridDim.x; b += 16)
+    for (unsigned b = group; b < gridDim.x; b += kGroups)
         s += __ldcg(&partials[((size_t)(panel * gridDim.x + b) * 2) * 8 + slot]);
     comb[group][slot] = s;
     __syncthreads();
     if (threadIdx.x < 16 && c < PW) {
         double t = 0.0;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) t += comb[g][threadIdx.x];
+        for (int g = 0; g < kGroups; ++g) t += comb[g][threadIdx.x];
         dots_step[(size_t)which * n_panels * PW + panel * PW + c] = t;
     }
     if (threadIdx.x == 0) tickets[panel] = 0u;
 }
 
 // ---- the fused step: FP64 warp-MMA formulation --------------------------------------------------
-template <int PW, bool FIRST>
-__global__ void __launch_bounds__(kThreads)
+// CH = neighbour blocks handled per round; the host picks the smallest instantiated CH that
+// covers the longest block row (5 for 2-D lattices, 7 for 3-D), so a row is ONE round:
+//   1. consume what earlier iterations prefetched (this row's block range and block columns),
+//   2. issue every load of the row back to back -- CH blocks, CH neighbour records, T_n and
+//      T_{n-1} of the row itself, and the index prefetches for the next rows,
+//   3. 2*CH MMAs, re/im exchange, update, dots, one store.
+// Straight-line code: slots past the end of a short row load a valid dummy address and feed
+// zeros to the MMA (no divergence handling, and no scoreboard slot shared between data that is
+// consumed now and loads that were issued just before -- the SASS has only six).
+template <int PW, bool FIRST, int CH>
+__global__ void __launch_bounds__(kThreads, 4)
 cheb_step_dmma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                const double2 *__restrict__ data, const double2 *__restrict__ x_cur, double2 *__restrict__ x_io,
                int n_sites, int rows_per_cta, double alpha, double beta, double *__restrict__ partials,
@@ -103,24 +132,137 @@ cheb_step_dmma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ i
     const int panel = blockIdx.y;
     const double2 *__restrict__ xc = x_cur + (size_t)panel * n_sites * REC;
     double2 *__restrict__ xo = x_io + (size_t)panel * n_sites * REC;
-    const int row_begin = blockIdx.x * rows_per_cta;
-    const int row_end = min(n_sites, row_begin + rows_per_cta);
+    // Row traversal: the whole grid sweeps the lattice as one wavefront -- in pass t, CTA b works on
+    // rows (t * gridDim.x + b) * kWarps ... + kWarps - 1.  All SMs then touch one window of a few
+    // thousand consecutive sites at a time, so the records of the +-Ly / +-LyLz neighbours (read
+    // again one or two passes later) are still in L2 and every vector byte leaves HBM once.
+    (void)rows_per_cta;
+    const int stride = gridDim.x * kWarps;
 
     // A-operand role: lanes 0-15 feed rows 0-3 of [[Br,-Bi],[Bi,Br]], lanes 16-31 rows 4-7.
     const int elem = lane & 15;
     const bool hi = lane >= 16;
-    // B-operand role: lane l holds record element l = (column l/4, alpha l%4).
+    // B-operand role: lane l holds record element l = (column l/4, alpha l%4); lanes past the
+    // record (PW < 8) read element 0 and contribute zeros.
     const bool x_lane = lane < REC;
+    const int x_elem = x_lane ? lane : 0;
     // Output role after the re/im exchange: lane owns T_{n+1}[row][alpha=a][column=col].
     const int a = (lane >> 2) & 3;
     const int col = 2 * (lane & 3) + (lane >> 4);
     const bool o_lane = col < PW;
-    const int o_elem = col * 4 + a;
+    const int o_elem = o_lane ? col * 4 + a : 0;
+
+    int row = blockIdx.x * kWarps + warp;
+    int p0 = 0, p1 = 0, q0 = 0, q1 = 0, jv = 0;  // [p0,p1): this row's blocks, [q0,q1): next row's
+    if (row < n_sites) {
+        p0 = __ldg(indptr + row);
+        p1 = __ldg(indptr + row + 1);
+    }
+    if (row + stride < n_sites) {
+        q0 = __ldg(indptr + row + stride);
+        q1 = __ldg(indptr + row + stride + 1);
+    }
+    if (lane < p1 - p0) jv = __ldg(indices + p0 + lane);
 
     double d0 = 0.0, d1 = 0.0;
-    for (int row = row_begin + warp; row < row_end; row += kWarps) {
+    for (; row < n_sites; row += stride) {
+        // (1) consume prefetched index data: neighbour ids of the first CH blocks
+        const int cnt = p1 - p0;
+        int jn_u[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int j = __shfl_sync(kFull, jv, u);
+            jn_u[u] = u < cnt ? j : row;  // dummy: the row's own record (always valid)
+        }
+        // (2) all loads of the row
+        double2 bv[CH], xv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int p = u < cnt ? p0 + u : p0;
+            bv[u] = ld_stream(data + (size_t)p * 16 + elem);
+            xv[u] = ld_reuse(xc + (size_t)jn_u[u] * REC + x_elem);
+        }
+        const size_t off = (size_t)row * REC + o_elem;
+        const double2 tn = ld_reuse(xc + off);
+        double2 pv = make_double2(0.0, 0.0);
+        if (!FIRST) pv = ld_plain(xo + off);
+        int r0 = 0, r1 = 0, jn = 0;
+        if (row + 2 * stride < n_sites) {
+            r0 = __ldg(indptr + row + 2 * stride);
+            r1 = __ldg(indptr + row + 2 * stride + 1);
+        }
+        if (lane < q1 - q0) jn = __ldg(indices + q0 + lane);
+
+        // (3) MMAs: two independent accumulation chains
+        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const bool live = u < cnt;
+            const double xr = (live && x_lane) ? xv[u].x : 0.0;
+            const double xi = (live && x_lane) ? xv[u].y : 0.0;
+            dmma_8x8x4(re0, re1, hi ? bv[u].y : bv[u].x, xr);   // [Br; Bi]  * Xr
+            dmma_8x8x4(im0, im1, hi ? bv[u].x : -bv[u].y, xi);  // [-Bi; Br] * Xi
+        }
+        // rows longer than CH blocks (generic lattices): plain loop over the rest
+        for (int t = CH; t < cnt; ++t) {
+            const int j = __ldg(indices + p0 + t);
+            const double2 b2 = __ldcs(data + (size_t)(p0 + t) * 16 + elem);
+            const double2 x2 = __ldg(xc + (size_t)j * REC + x_elem);
+            dmma_8x8x4(re0, re1, hi ? b2.y : b2.x, x_lane ? x2.x : 0.0);
+            dmma_8x8x4(im0, im1, hi ? b2.x : -b2.y, x_lane ? x2.y : 0.0);
+        }
+        const double c0 = re0 + im0, c1 = re1 + im1;
+        // Lanes < 16 hold Re(y) of (a, columns 2q, 2q+1), lanes >= 16 the matching Im(y):
+        // swap one value with the partner lane so each lane owns one complex element.
+        const double recv = __shfl_xor_sync(kFull, hi ? c0 : c1, 16);
+        const double yr = hi ? recv : c0;
+        const double yi = hi ? c1 : recv;
+        if (o_lane) {
+            const double2 out = make_double2(alpha * yr - beta * pv.x, alpha * yi - beta * pv.y);
+            xo[off] = out;
+            d0 += tn.x * tn.x + tn.y * tn.y;
+            d1 += out.x * tn.x + out.y * tn.y;
+        }
+        p0 = q0; p1 = q1; jv = jn;
+        q0 = r0; q1 = r1;
+    }
+    // lanes sharing a column differ in alpha (lane bits 2,3)
+    d0 += __shfl_xor_sync(kFull, d0, 4);
+    d1 += __shfl_xor_sync(kFull, d1, 4);
+    d0 += __shfl_xor_sync(kFull, d0, 8);
+    d1 += __shfl_xor_sync(kFull, d1, 8);
+    finish_dots<PW>(d0, d1, col, o_lane && a == 0, panel, n_panels, partials, tickets, dots_step);
+}
+
+// ---- unpipelined variant of the MMA formulation (tuning reference) ----------------------------
+template <int PW, bool FIRST>
+__global__ void __launch_bounds__(kThreads)
+cheb_step_dmma_simple(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                      const double2 *__restrict__ data, const double2 *__restrict__ x_cur,
+                      double2 *__restrict__ x_io, int n_sites, int rows_per_cta, double alpha, double beta,
+                      double *__restrict__ partials, unsigned *__restrict__ tickets, double *__restrict__ dots_step,
+                      int n_panels) {
+    constexpr int REC = PW * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int panel = blockIdx.y;
+    const double2 *__restrict__ xc = x_cur + (size_t)panel * n_sites * REC;
+    double2 *__restrict__ xo = x_io + (size_t)panel * n_sites * REC;
+    const int elem = lane & 15;
+    const bool hi = lane >= 16;
+    const bool x_lane = lane < REC;
+    const int a = (lane >> 2) & 3;
+    const int col = 2 * (lane & 3) + (lane >> 4);
+    const bool o_lane = col < PW;
+    const int o_elem = col * 4 + a;
+    // rows_per_cta > 0: every CTA walks its own contiguous range; == 0: wavefront traversal
+    const int row_first = rows_per_cta > 0 ? blockIdx.x * rows_per_cta + warp : blockIdx.x * kWarps + warp;
+    const int row_end = rows_per_cta > 0 ? min(n_sites, (int)(blockIdx.x + 1) * rows_per_cta) : n_sites;
+    const int stride = rows_per_cta > 0 ? kWarps : gridDim.x * kWarps;
+
+    double d0 = 0.0, d1 = 0.0;
+    for (int row = row_first; row < row_end; row += stride) {
         const int p0 = indptr[row], p1 = indptr[row + 1];
-        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;  // two independent accumulation chains
+        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
         for (int pb = p0; pb < p1; pb += 32) {
             const int cnt = min(32, p1 - pb);
             const int jv = lane < cnt ? indices[pb + lane] : 0;
@@ -130,13 +272,11 @@ cheb_step_dmma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ i
                 const double2 bv = __ldcs(data + (size_t)(pb + t) * 16 + elem);
                 double2 xv = make_double2(0.0, 0.0);
                 if (x_lane) xv = __ldg(xc + (size_t)j * REC + lane);
-                dmma_8x8x4(re0, re1, hi ? bv.y : bv.x, xv.x);   // [Br; Bi]  * Xr
-                dmma_8x8x4(im0, im1, hi ? bv.x : -bv.y, xv.y);  // [-Bi; Br] * Xi
+                dmma_8x8x4(re0, re1, hi ? bv.y : bv.x, xv.x);
+                dmma_8x8x4(im0, im1, hi ? bv.x : -bv.y, xv.y);
             }
         }
         const double c0 = re0 + im0, c1 = re1 + im1;
-        // Lanes < 16 hold Re(y) of (a, columns 2q, 2q+1), lanes >= 16 the matching Im(y):
-        // swap one value with the partner lane so each lane owns one complex element.
         const double recv = __shfl_xor_sync(kFull, hi ? c0 : c1, 16);
         const double yr = hi ? recv : c0;
         const double yi = hi ? c1 : recv;
@@ -155,7 +295,6 @@ cheb_step_dmma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ i
             d1 += out.x * tn.x + out.y * tn.y;
         }
     }
-    // lanes sharing a column differ in alpha (lane bits 2,3)
     d0 += __shfl_xor_sync(kFull, d0, 4);
     d1 += __shfl_xor_sync(kFull, d1, 4);
     d0 += __shfl_xor_sync(kFull, d0, 8);
@@ -176,14 +315,14 @@ cheb_step_fma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ in
     const int panel = blockIdx.y;
     const double2 *__restrict__ xc = x_cur + (size_t)panel * n_sites * REC;
     double2 *__restrict__ xo = x_io + (size_t)panel * n_sites * REC;
-    const int row_begin = blockIdx.x * rows_per_cta;
-    const int row_end = min(n_sites, row_begin + rows_per_cta);
+    (void)rows_per_cta;  // same wavefront traversal as cheb_step_dmma
     const int col = lane % PW, sub = lane / PW;
 
     double d0 = 0.0, d1 = 0.0;
-    for (int base = row_begin + warp * ROWS_PER_WARP; base < row_end; base += kWarps * ROWS_PER_WARP) {
+    for (int base = (blockIdx.x * kWarps + warp) * ROWS_PER_WARP; base < n_sites;
+         base += gridDim.x * kWarps * ROWS_PER_WARP) {
         const int row = base + sub;
-        if (row >= row_end) continue;
+        if (row >= n_sites) continue;
         double2 acc[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r] = make_double2(0.0, 0.0);
@@ -295,17 +434,22 @@ unpack_vectors(const double2 *__restrict__ x, int n_sites, int pw, int n_cols, d
 using StepKernel = void (*)(const int32_t *, const int32_t *, const double2 *, const double2 *, double2 *, int, int,
                             double, double, double *, unsigned *, double *, int);
 
-template <int PW> StepKernel pick_pw(int kernel, bool first) {
+template <int PW> StepKernel pick_pw(int kernel, bool first, int max_row) {
     if (kernel == BDG_KERNEL_FMA) return first ? cheb_step_fma<PW, true> : cheb_step_fma<PW, false>;
-    return first ? cheb_step_dmma<PW, true> : cheb_step_dmma<PW, false>;
+    if (kernel == BDG_KERNEL_DMMA_SIMPLE || kernel == BDG_KERNEL_DMMA_CHUNKED)
+        return first ? cheb_step_dmma_simple<PW, true> : cheb_step_dmma_simple<PW, false>;
+    if (max_row <= 3) return first ? cheb_step_dmma<PW, true, 3> : cheb_step_dmma<PW, false, 3>;
+    if (max_row <= 5) return first ? cheb_step_dmma<PW, true, 5> : cheb_step_dmma<PW, false, 5>;
+    if (max_row <= 7) return first ? cheb_step_dmma<PW, true, 7> : cheb_step_dmma<PW, false, 7>;
+    return first ? cheb_step_dmma<PW, true, 8> : cheb_step_dmma<PW, false, 8>;
 }
 
-StepKernel pick_kernel(int kernel, int pw, bool first) {
+StepKernel pick_kernel(int kernel, int pw, bool first, int max_row) {
     switch (pw) {
-        case 1: return pick_pw<1>(kernel, first);
-        case 2: return pick_pw<2>(kernel, first);
-        case 4: return pick_pw<4>(kernel, first);
-        default: return pick_pw<8>(kernel, first);
+        case 1: return pick_pw<1>(kernel, first, max_row);
+        case 2: return pick_pw<2>(kernel, first, max_row);
+        case 4: return pick_pw<4>(kernel, first, max_row);
+        default: return pick_pw<8>(kernel, first, max_row);
     }
 }
 
@@ -317,8 +461,8 @@ int launch_step(bdg_system *sys, bool first) {
     double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
     const double2 *x_cur = st.vec[st.cur].as<double2>();
     double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
-    const int rows_per_cta = (int)ceil_div(m.n_sites, st.grid_x);
-    StepKernel k = pick_kernel(st.kernel, st.panel_width, first);
+    const int rows_per_cta = st.kernel == BDG_KERNEL_DMMA_CHUNKED ? (int)ceil_div(m.n_sites, st.grid_x) : 0;
+    StepKernel k = pick_kernel(st.kernel, st.panel_width, first, sys->packed_max_row);
     dim3 grid((unsigned)st.grid_x, (unsigned)st.n_panels);
     k<<<grid, kThreads, 0, sys->stream>>>(m.indptr.as<int32_t>(), m.indices.as<int32_t>(), m.data.as<double2>(), x_cur,
                                           x_io, (int)m.n_sites, rows_per_cta, (first ? 1.0 : 2.0) / st.scale,
@@ -377,7 +521,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_DMMA || kernel == BDG_KERNEL_FMA, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DMMA_CHUNKED && kernel != 3, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;
@@ -400,7 +544,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
     // walks one contiguous range of block rows (neighbouring rows share their X records in L1).
     int per_sm = 1;
-    BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(st.kernel, st.panel_width, false), kThreads, 0));
+    BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(st.kernel, st.panel_width, false, sys->packed_max_row), kThreads, 0));
     per_sm = std::max(per_sm, 1);
     const int64_t target = (int64_t)sys->sm_count * per_sm;
     int64_t gx = std::max<int64_t>(1, target / st.n_panels);

@@ -7,7 +7,7 @@ import bodge_b200 as b
 from bodge_b200 import workloads
 
 PEAK = 6459.3
-def run(cfg, k, kernels=("dmma", "fma"), steps=50):
+def run(cfg, k, kernels=("dmma", "dmma_simple", "fma"), steps=50):
     c = workloads.CONFIGS[cfg]
     t0 = time.time()
     packed = c["build"](c["shape"])
@@ -31,5 +31,5 @@ def run(cfg, k, kernels=("dmma", "fma"), steps=50):
         s.cheb_end()
 
 if __name__ == "__main__":
-    for cfg, k in [("C5", 8), ("C5", 1), ("C4", 8), ("C2", 256), ("C3", 512), ("C5", 16), ("C5", 4)]:
+    for cfg, k in [("C5", 8), ("C4", 8), ("C2", 256), ("C3", 512), ("C5", 1), ("C5", 4), ("C5", 16)]:
         run(cfg, k)

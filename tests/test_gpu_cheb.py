@@ -131,13 +131,13 @@ def test_free_energy_C1_exact_trace(gpu_api, observables):
     """Config C1 (40x40): all 6400 unit columns, vs the reference's dense value at T = 0.1."""
     system = cases.readme_swave(gpu_api, (40, 40, 1))
     temps, F_ref = observables["temps"], observables["F_C1"]
-    F = system.free_energy(0.1, cuda=True)
-    assert abs(F - F_ref[list(temps).index(0.1)]) <= TOL * abs(F)
-    F = system.free_energy(1.0, cuda=True)
-    assert abs(F - F_ref[list(temps).index(1.0)]) <= TOL * abs(F)
+    F01 = system.free_energy(0.1, cuda=True)
+    assert abs(F01 - F_ref[list(temps).index(0.1)]) <= TOL * abs(F01)
+    F10 = system.free_energy(1.0, cuda=True)
+    assert abs(F10 - F_ref[list(temps).index(1.0)]) <= TOL * abs(F10)
     # stochastic trace: unbiased estimate, error ~ 1/sqrt(R * 4N)
     Fs = system.free_energy(0.1, cuda=True, vectors=64, seed=1234)
-    assert abs(Fs - F) <= 2e-3 * abs(F)
+    assert abs(Fs - F01) <= 1e-2 * abs(F01)
 
 
 @pytest.mark.parametrize("tag,site", [("readme_12_12_1", (6, 6, 0)), ("random_5_5_2", (2, 3, 1)), ("dwave_9_8_1", (4, 4, 0))])
