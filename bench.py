@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused Chebyshev H·X steps on a 10^6-site BdG Hamiltonian.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C5] [--cols 8]
+
+One "step" = one pass of the fused kernel T_{n+1} = 2 H~ T_n - T_{n-1} (+ the two moment dot
+products) over one tile of ``cols`` vectors (default 8) per GPU, i.e. one HBM pass over the
+matrix and the vectors.  Workload: BASELINE.json config C5, CubicLattice((1000,1000,1))
+altermagnet/superconductor Josephson junction, 10^6 sites, 4,996,000 BSR blocks, synthetic
+(SURVEY 8d).  N > 1: one process per GPU (torchrun), a replica of the matrix and its own 8 columns
+on every GPU (weak scaling), one NCCL all-reduce of the moments at the end of the timed region.
+
+Prints ONE JSON line (see the task contract): ``value`` = whole-job steps/s with everything
+resident in HBM; ``e2e`` = the same metric through the public API with the Hamiltonian terms in
+pinned HOST memory (upload + scatter + recursion + moments back to the host inside the timed
+region); ``roofline`` = algorithmic bytes per step / measured kernel time vs the measured HBM
+peak; ``cpu_baseline`` = scipy's bsr_matvecs recursion on the host cores (oracle port).
+
+``--impl reference`` times only that CPU path (rank 0), on the same config/metric/unit.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "chebyshev_spmm_steps_per_s"
+UNIT = "steps/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C5")
+    ap.add_argument("--cols", type=int, default=8, help="vector columns per GPU")
+    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload_key):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload_key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi sampled in the background during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: scipy bsr_matvecs recursion on the host (oracle port)
+# ------------------------------------------------------------------------------------------
+def cpu_chebyshev(cfg_key, cols, steps, warmup, budget_s):
+    from bodge_b200 import workloads
+    from oracle import bdg_oracle as orc
+    from oracle import cpu_baseline as cb
+
+    cfg = workloads.CONFIGS[cfg_key]
+    t0 = time.perf_counter()
+    packed = cfg["build"](cfg["shape"])
+    ptr, idx, dat = cb.assemble(cfg["shape"], packed)
+    t_asm = time.perf_counter() - t0
+    scale = 1.01 * orc.norm_inf(ptr, idx, dat)
+    x0 = orc.rademacher(1234, 4 * (len(ptr) - 1), np.arange(cols))
+    res = cb.time_steps(ptr, idx, dat, scale, x0, steps=steps, warmup=warmup, budget_s=budget_s)
+    res["assembly_s"] = t_asm
+    res["n_sites"] = len(ptr) - 1
+    res["n_blocks"] = len(idx)
+    return res
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bodge_b200 import workloads
+
+    cfg = workloads.CONFIGS[args.config]
+    res = cpu_chebyshev(args.config, args.cols, args.steps, args.warmup, budget_s=120.0)
+    value = 1e3 / res["ms_per_step"]
+    sample = (f"{args.steps} steps after {args.warmup} warm-up on {res['fraction']:.3f} of the block rows per step "
+              f"(time scaled to a full step), k={args.cols}, rows split over {res['cores']} processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["label"], "config": args.config, "n_sites": res["n_sites"], "n_blocks": res["n_blocks"],
+                   "cols_per_gpu": args.cols, "what": "scipy bsr_matvecs recursion 2*(H~@T1)-T0 on the host (oracle port of the reference path)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workloads.CONFIGS[args.config]
+    shape, cols, K, W = cfg["shape"], args.cols, args.steps, args.warmup
+
+    # ---- inputs: Hamiltonian terms as packed arrays in pinned host memory --------------------
+    packed = cfg["build"](shape)
+    pinned = []
+    for arr in packed:
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        pinned.append(t)
+    host = [t.numpy() for t in pinned]
+    h2d_bytes = sum(a.nbytes for a in host)
+
+    # ---- assembly (timed separately: the second half of BASELINE.json's metric) ---------------
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    system = b.Hamiltonian(b.CubicLattice(shape), device=local)
+    system._sys.sync()
+    t1 = time.perf_counter()
+    max_dev = system.fill(*host)
+    info0 = system._sys.cheb_info()  # builds the compacted BSR the Chebyshev engine consumes
+    system._sys.sync()
+    t2 = time.perf_counter()
+    n_sites = system.lattice.size
+    assembly = {
+        "sites_per_s": n_sites / (t2 - t0), "unit": "sites/s", "n_sites": n_sites, "n_blocks": info0["n_blocks"],
+        "skeleton_s": t1 - t0, "scatter_check_compact_s": t2 - t1, "h2d_bytes": h2d_bytes, "hermitian_dev": max_dev,
+        "what": "bdg_create_cubic + bdg_scatter (pinned host arrays -> device, symmetry fill, Hermitian check) + zero-block compaction",
+    }
+
+    scale = system.spectral_bound()
+    s = system._sys
+    stream = torch.cuda.current_stream()
+    s.set_stream(stream.cuda_stream)
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    s.cheb_begin(n_random=cols, seed=1234, col_offset=rank * cols, scale=scale, kernel=args.kernel)
+    s.cheb_reserve(W + K + 8)
+    mu_dev = torch.empty(2 * (W + K + 1), dtype=torch.float64, device=f"cuda:{local}")
+    s.cheb_steps(W)
+    info = s.cheb_info()
+    launches0 = info["launches"]
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        s.cheb_steps(K)
+        e1.record(stream)
+        # the single exchange of the path: combine the moments of all column shards
+        n_mom = 2 * (W + K + 1)
+        s.cheb_read(n_mom, cols, summed=True, device_ptr=mu_dev.data_ptr())
+        if world > 1:
+            dist.all_reduce(mu_dev[:n_mom])
+        e2.record(stream)
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    kernel_ms = e0.elapsed_time(e1)
+    total_ms = e0.elapsed_time(e2)
+    times = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = (float(v) for v in times.cpu())
+    launches = s.cheb_info()["launches"] - launches0
+    mu0 = float(mu_dev[0].cpu())
+    assert abs(mu0 - 4.0 * n_sites * cols * world) < 1e-6 * mu0, "moment 0 must equal the number of vector entries"
+
+    # ---- end to end through the public API with host buffers -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        s.set_stream(None)
+        e2e_steps = 1024  # 2050 moments: the recursion length of the C5 free-energy evaluation
+        calls = 2
+
+        def one_call():
+            system.fill(*host)  # H2D of all Hamiltonian terms + scatter + Hermitian check
+            mu = system.chebyshev_moments(2 * e2e_steps + 2, vectors=cols * world, seed=1234, summed=True, kernel=args.kernel)
+            return mu  # host numpy (D2H inside)
+
+        one_call()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            mu = one_call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.cpu())
+        e2e = {"value": world * calls * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": h2d_bytes / e2e_steps, "d2h_bytes_per_step": mu.nbytes / e2e_steps,
+               "what": f"{calls} x [Hamiltonian.fill(pinned host arrays) + chebyshev_moments({2 * e2e_steps + 2}) -> host]; "
+                       f"{e2e_steps} steps per call", "seconds": dt}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    bytes_step = info["bytes_per_step"]
+    achieved = bytes_step * K / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(f"{args.config}_k{cols}"), "peak_source": peak_src,
+                "kernel": "cheb_step_dmma", "algorithmic_bytes_per_launch": bytes_step,
+                "kernel_ms_per_launch": kernel_ms / K}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        res = cpu_chebyshev(args.config, cols, steps=3, warmup=1, budget_s=20.0)
+        cpu = {"value": 1e3 / res["ms_per_step"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+               "sample": f"3 steps after 1 warm-up of the same workload (k={cols}) on {res['fraction']:.3f} of the block rows, "
+                         f"scipy bsr_matvecs, rows split over {res['cores']} processes; numpy assembly took {res['assembly_s']:.1f} s",
+               "assembly_sites_per_s": res["n_sites"] / res["assembly_s"]}
+
+    line = {
+        "metric": METRIC, "value": world * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": cfg["label"], "config": args.config, "n_sites": n_sites, "n_blocks": info["n_blocks"],
+                   "cols_per_gpu": cols, "parallelism": f"column shards x{world}, matrix replicated",
+                   "l2": "inputs (1.3 GB matrix + 1.0 GB vectors) exceed the 126 MB L2; no flush needed",
+                   "kernel": args.kernel, "panel_width": info["panel_width"]},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "assembly": assembly,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

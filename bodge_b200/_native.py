@@ -48,6 +48,7 @@ SIGNATURES = {
     "bdg_norm_inf": [_vp, _f64p],
     "bdg_cheb_begin": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int],
     "bdg_cheb_steps": [_vp, C.c_int32, C.POINTER(C.c_float)],
+    "bdg_cheb_reserve": [_vp, C.c_int32],
     "bdg_cheb_available": [_vp, C.POINTER(C.c_int32)],
     "bdg_cheb_moments_read": [_vp, C.c_int32, C.c_int, _vp, C.c_int],
     "bdg_cheb_moments": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int32, C.c_int, _vp, C.c_int],
@@ -228,6 +229,9 @@ class System:
         ms = C.c_float(0.0)
         check(load().bdg_cheb_steps(self._h, int(n_steps), C.byref(ms) if timed else None))
         return ms.value if timed else None
+
+    def cheb_reserve(self, n_steps: int):
+        check(load().bdg_cheb_reserve(self._h, int(n_steps)))
 
     def cheb_available(self) -> int:
         n = C.c_int32()

@@ -607,6 +607,13 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
     return BDG_OK;
 }
 
+extern "C" int bdg_cheb_reserve(bdg_t *sys, int32_t n_steps) {
+    BDG_ENTER(sys);
+    BDG_REQUIRE(sys->cheb.active, "bdg_cheb_begin has not been called");
+    BDG_REQUIRE(n_steps >= 0, "negative step count");
+    return ensure_dot_capacity(sys, sys->cheb.steps_done + n_steps);
+}
+
 extern "C" int bdg_cheb_available(bdg_t *sys, int32_t *n_moments) {
     BDG_REQUIRE(sys && n_moments, "null argument");
     *n_moments = sys->cheb.active ? 2 * (sys->cheb.steps_done + 1) : 0;

@@ -118,6 +118,9 @@ int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_ro
  * elapsed_ms != NULL: bracket the steps with CUDA events on the handle's stream, synchronise,
  * and return the device time. */
 int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms);
+/* Pre-size the dot-product storage for n_steps further steps (bdg_cheb_steps grows it on demand,
+ * which costs an allocation and a stream synchronisation the first time). */
+int bdg_cheb_reserve(bdg_t *sys, int32_t n_steps);
 /* Moments available so far: 2 * (steps + 1). */
 int bdg_cheb_available(bdg_t *sys, int32_t *n_moments);
 /* mu[n * n_out + c], n < n_moments; n_out = n_cols (BDG_MU_PER_COLUMN) or 1 (BDG_MU_SUM, summed

@@ -1,0 +1,125 @@
+"""Host logic that needs no GPU: dict packing, KPM post-processing against the oracle's
+formulas, packed workloads against the dict API (via the recorder), the C-ABI library's symbols,
+loud failure without a device, column sharding."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bodge_b200 as b
+import cases
+from bodge_b200 import _native, distributed, kpm, workloads
+from bodge_b200.hamiltonian import _pack_entries
+from oracle import bdg_oracle as orc
+from util import oracle_assemble, same_bits
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pack_entries():
+    lat = b.CubicLattice((3, 4, 5))
+    d = {((0, 0, 0), (0, 0, 1)): b.σ1, ((2, 3, 4), (2, 3, 4)): 2 * b.σ0 - 1j * b.σ2}
+    i, j, v = _pack_entries(lat, d)
+    assert i.tolist() == [0, 59] and j.tolist() == [1, 59]
+    assert v.shape == (2, 2, 2) and np.array_equal(v[1], 2 * b.σ0 - 1j * b.σ2)
+    i, j, v = _pack_entries(lat, {})
+    assert len(i) == 0 and v.shape == (0, 2, 2)
+    with pytest.raises(ValueError):
+        _pack_entries(lat, {((0, 0, 0), (0, 0, 5)): b.σ0})
+    with pytest.raises(TypeError):
+        _pack_entries(lat, {(0, 1): b.σ0})
+    # broadcastable values, as numpy assignment in the reference would accept
+    i, j, v = _pack_entries(lat, {((0, 0, 0), (0, 0, 0)): 3.0, ((1, 0, 0), (1, 0, 0)): b.σ3})
+    assert np.array_equal(v[0], np.full((2, 2), 3.0))
+
+
+@pytest.mark.parametrize("name,shape", [("readme_swave", (7, 6, 1)), ("dwave_rashba", (6, 7, 1)),
+                                         ("swave_3d", (4, 5, 3)), ("junction", (12, 5, 1)), ("junction", (9, 4, 2))])
+def test_packed_workloads_equal_dict_api(name, shape):
+    """Vectorised builders (used at 10^6 sites) == the dict-API models, through the oracle."""
+    rec = getattr(cases, name)(cases.recorder_api(), shape)
+    (_, _, sd1), ex1 = oracle_assemble(shape, [rec.packed()])
+    (_, _, sd2), ex2 = oracle_assemble(shape, [tuple(np.asarray(a) for a in getattr(workloads, name)(shape))])
+    assert same_bits(sd1, sd2)
+    for a, c in zip(ex1, ex2):
+        assert same_bits(a, c)
+
+
+def test_kpm_postprocessing_matches_oracle():
+    rng = np.random.default_rng(0)
+    mu = rng.standard_normal(300) * np.exp(-np.arange(300) / 60.0)
+    for T in (0.0, 0.03, 0.4):
+        assert np.isclose(kpm.free_energy_from_trace(mu, T, 7.3), orc.free_energy_from_moments(mu, T, 7.3), rtol=1e-13)
+    with pytest.raises(ValueError):
+        kpm.free_energy_from_trace(mu, -0.1, 7.3)
+    for z in (0.3 + 0.05j, -0.7 + 0.01j, 0.0 + 0.2j, 0.2 - 0.1j):
+        assert np.isclose(kpm.resolvent_diagonal(mu, z), orc.resolvent_from_moments(mu, z), rtol=1e-11)
+    mu4 = np.abs(rng.standard_normal((400, 4))) * np.exp(-np.arange(400) / 50.0)[:, None]
+    E = [-0.5, -0.1, 0.0, 0.1, 0.5, 0.9]
+    assert np.allclose(kpm.ldos_from_site_moments(mu4, E, 5.0), orc.ldos_from_moments(mu4, E, 5.0), rtol=1e-11)
+    # Chebyshev coefficients reproduce the function
+    c = kpm.chebyshev_coefficients(lambda e: kpm.free_energy_density(e, 0.3), 200, 4.0)
+    x = np.linspace(-0.99, 0.99, 41)
+    series = np.polynomial.chebyshev.chebval(x, c)
+    assert np.allclose(series, kpm.free_energy_density(4.0 * x, 0.3), atol=1e-12)
+    assert kpm.default_moments(0.1, 7.2) % 2 == 0 and 600 < kpm.default_moments(0.1, 7.2) < 900
+    assert kpm.ldos_moments_needed(7.0, 0.01) % 2 == 0
+
+
+def test_resolvent_of_known_spectrum():
+    """Moments of a single eigenvalue x0 are T_n(x0): the series must give 1/(z - x0)."""
+    x0 = 0.37
+    mu = np.cos(np.arange(4000) * np.arccos(x0))
+    for z in (0.1 + 0.02j, 0.37 + 0.01j, -0.9 + 0.03j):
+        assert np.isclose(kpm.resolvent_diagonal(mu, z), 1 / (z - x0), rtol=1e-9)
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """libbdg.so loads and exports exactly what include/bdg.h declares (no compute calls)."""
+    header = open(os.path.join(REPO, "include", "bdg.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*\*?(bdg_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    assert os.path.exists(_native.LIB_PATH), "run `python -m bodge_b200.build` (or __graft_entry__.build()) first"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in bdg.h but not exported"
+    assert declared - {"bdg_last_error"} == set(_native.SIGNATURES), "ctypes table and header disagree"
+    loaded = _native.load()
+    assert loaded.bdg_abi_version() == 1
+    assert isinstance(_native.last_error(), str)
+
+
+def test_fails_loudly_without_device_or_library(monkeypatch):
+    if _native.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b.Hamiltonian(b.CubicLattice((3, 3, 1)))
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libbdg.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b.Hamiltonian(b.CubicLattice((3, 3, 1)))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "bodge_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_shard_range():
+    for n, world in [(64, 8), (10, 4), (3, 8), (0, 2), (4096, 3)]:
+        spans = [distributed.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == c[0] for a, c in zip(spans[:-1], spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert distributed.resolve(None) == (0, 1, None)
+    assert distributed.resolve("auto")[:2] == (0, 1)
+    local = np.arange(6.0).reshape(3, 2)
+    assert distributed.combine(local, False, 2, 0, 1) is local

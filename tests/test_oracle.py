@@ -147,7 +147,7 @@ def test_free_energy_from_moments_matches_reference(observables, structures, tag
     scale = 1.01 * orc.norm_inf(ptr, idx, dat)
     temps, want = observables["temps"], observables[f"F_{tag}"]
     n_rows = H.shape[0]
-    n_mom = 1200
+    n_mom = 900
     mu = orc.cheb_moments_doubling(H, np.eye(n_rows, dtype=np.complex128), n_mom, scale).sum(axis=1)
     for T, F_ref in zip(temps, want):
         F = orc.free_energy_from_moments(mu, float(T), scale)
