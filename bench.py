@@ -217,7 +217,8 @@ def run_ours(args):
 
     scale = system.spectral_bound()
     s = system._sys
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)  # the library launches on this stream; events are recorded on it
+    torch.cuda.set_stream(stream)
     s.set_stream(stream.cuda_stream)
 
     # ---- device-resident timing ------------------------------------------------------------------

@@ -161,7 +161,13 @@ class System:
 
     # -- plumbing ---------------------------------------------------------------------------
     def set_stream(self, stream_ptr: int | None):
-        check(load().bdg_set_stream(self._h, _vp(stream_ptr) if stream_ptr else None))
+        """Borrow a CUDA stream given as an integer handle (``torch.cuda.Stream.cuda_stream``);
+        ``None`` restores the handle's own stream.  Handle 0 is CUDA's legacy default stream,
+        which the C ABI spells ``cudaStreamLegacy`` (0x1) because NULL means "own stream"."""
+        if stream_ptr is None:
+            check(load().bdg_set_stream(self._h, None))
+        else:
+            check(load().bdg_set_stream(self._h, _vp(stream_ptr if stream_ptr != 0 else 1)))
 
     def sync(self):
         check(load().bdg_sync(self._h))
