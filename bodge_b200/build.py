@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbdg.so")
-SOURCES = ["assemble.cu", "scan.cu", "cheb.cu"]
+SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu"]
 
 
 def nvcc_path() -> str:
@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     cmd = [
-        nvcc_path(), "-O3", "-std=c++17", "-lineinfo",
+        nvcc_path(), "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,

@@ -78,7 +78,22 @@ struct ChebState {
     DevBuf tickets;   // uint32 [n_panels] arrival counters (last CTA reduces)
     DevBuf mu_tmp;    // staging for moment read-out
     int grid_x = 0;
+    int panels_per_group = 1;  // ELL kernel: panels sharing one pass over the matrix (grid.y = groups)
+    int n_groups = 0;
     int64_t launches = 0;
+};
+
+// Kernel-native copy of the packed matrix for the ELL step kernel (cheb_ell.cu): every block row
+// padded to `width` slots, slot 0 = the diagonal block (zero block if absent), then the other
+// blocks in ascending column order; padding slots are zero blocks pointing at the row itself.
+//   idx  int32  [n_sites][width]
+//   data double [n_sites][width][4 (a)][2 (re, im)][4 (b)]   -- MMA B-fragment order, 256 B/block
+struct EllDev {
+    bool valid = false;
+    bool usable = false;   // false: rows too long / too ragged, use the generic kernel
+    int width = 0;
+    int64_t n_sites = 0;
+    DevBuf idx, data;
 };
 
 struct bdg_system {
@@ -99,6 +114,7 @@ struct bdg_system {
     void *host_scalars = nullptr;  // pinned mirror
 
     ChebState cheb;
+    EllDev ell;
 };
 
 // scan.cu
@@ -112,5 +128,11 @@ int ensure_scratch(bdg_system *sys, int which, size_t bytes);
 // cheb.cu
 void cheb_release(bdg_system *sys);     // free all Chebyshev buffers
 void cheb_deactivate(bdg_system *sys);  // matrix changed: recursion state is stale, keep buffers
+
+// cheb_ell.cu
+int ell_build(bdg_system *sys);                    // (re)build sys->ell from sys->packed when stale
+int ell_configure(bdg_system *sys);                // pick panels_per_group / grid for the current ChebState
+int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
+void ell_release(bdg_system *sys);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

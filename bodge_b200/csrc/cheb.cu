@@ -25,91 +25,10 @@
 #include <cstring>
 
 #include "bdg_internal.h"
+#include "cheb_device.cuh"
 
 namespace {
 
-constexpr int kWarps = 4;  // 128-thread CTAs: finer occupancy granularity at ~96 registers/thread
-constexpr int kThreads = kWarps * 32;
-constexpr int kGroups = kThreads / 16;  // strided CTA groups in the last-CTA reduction
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-// 128-bit global loads as volatile asm: together with the (volatile) MMAs this pins the program
-// order "all loads of a row, then all MMAs", which the compiler otherwise interleaves to save
-// registers -- turning one HBM round trip per row into two or three.
-__device__ __forceinline__ double2 ld_stream(const double2 *p) {  // read-once data (matrix blocks)
-    double2 v;
-    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ld_reuse(const double2 *p) {  // vector records (re-read by neighbours)
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ld_plain(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
-// ---- per-step reduction of the two dot products ---------------------------------------------
-// Every lane arrives with its partial sums for column `col` (valid iff col_ok and it is the
-// designated leader lane for that column inside the warp).  CTA partials go to global memory;
-// the last CTA of a panel to arrive adds them up in a fixed order (deterministic results) and
-// writes the step's dot products.
-template <int PW>
-__device__ __forceinline__ void finish_dots(double d0, double d1, int col, bool leader, int panel, int n_panels,
-                                            double *__restrict__ partials, unsigned *__restrict__ tickets,
-                                            double *__restrict__ dots_step) {
-    __shared__ double red[kWarps][2][8];
-    __shared__ double comb[kGroups][16];
-    __shared__ bool is_last;
-    const int warp = threadIdx.x >> 5;
-    if (leader) {
-        red[warp][0][col] = d0;
-        red[warp][1][col] = d1;
-    }
-    __syncthreads();
-    const int which = (threadIdx.x >> 3) & 1, c = threadIdx.x & 7;
-    if (threadIdx.x < 16 && c < PW) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w][which][c];
-        partials[((size_t)(panel * gridDim.x + blockIdx.x) * 2 + which) * 8 + c] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // 16 (which, column) slots x kGroups strided groups of CTAs, then a fixed-order combine.
-    const int slot = threadIdx.x & 15, group = threadIdx.x >> 4;
-    double s = 0.0;
-    for (unsigned b = group; b < gridDim.x; b += kGroups)
-        s += __ldcg(&partials[((size_t)(panel * gridDim.x + b) * 2) * 8 + slot]);
-    comb[group][slot] = s;
-    __syncthreads();
-    if (threadIdx.x < 16 && c < PW) {
-        double t = 0.0;
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) t += comb[g][threadIdx.x];
-        dots_step[(size_t)which * n_panels * PW + panel * PW + c] = t;
-    }
-    if (threadIdx.x == 0) tickets[panel] = 0u;
-}
 
 // ---- the fused step: FP64 warp-MMA formulation --------------------------------------------------
 // CH = neighbour blocks handled per round; the host picks the smallest instantiated CH that
@@ -461,6 +380,12 @@ int launch_step(bdg_system *sys, bool first) {
     double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
     const double2 *x_cur = st.vec[st.cur].as<double2>();
     double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
+    if (st.kernel == BDG_KERNEL_ELL) {
+        BDG_TRY(ell_launch_step(sys, first, x_cur, x_io, dots_step));
+        st.cur ^= 1;
+        st.launches += 1;
+        return BDG_OK;
+    }
     const int rows_per_cta = st.kernel == BDG_KERNEL_DMMA_CHUNKED ? (int)ceil_div(m.n_sites, st.grid_x) : 0;
     StepKernel k = pick_kernel(st.kernel, st.panel_width, first, sys->packed_max_row);
     dim3 grid((unsigned)st.grid_x, (unsigned)st.n_panels);
@@ -494,7 +419,10 @@ int ensure_dot_capacity(bdg_system *sys, int steps_total) {
 
 }  // namespace
 
-void cheb_deactivate(bdg_system *sys) { sys->cheb.active = false; }
+void cheb_deactivate(bdg_system *sys) {
+    sys->cheb.active = false;
+    sys->ell.valid = false;
+}
 
 void cheb_release(bdg_system *sys) {
     ChebState &st = sys->cheb;
@@ -505,6 +433,7 @@ void cheb_release(bdg_system *sys) {
     dev_free(sys, st.partials);
     dev_free(sys, st.tickets);
     dev_free(sys, st.mu_tmp);
+    ell_release(sys);
     const int64_t launches = st.launches;
     st = ChebState();
     st.launches = launches;
@@ -521,8 +450,14 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DMMA_CHUNKED && kernel != 3, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DMMA_CHUNKED, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
+    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL) {
+        BDG_TRY(ell_build(sys));
+        BDG_REQUIRE(kernel == BDG_KERNEL_AUTO || sys->ell.usable,
+                    "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");
+        kernel = sys->ell.usable ? BDG_KERNEL_ELL : BDG_KERNEL_DMMA;
+    }
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;
     if (kind == BDG_X0_PROBE)
@@ -532,7 +467,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     // Buffers of a previous recursion are kept and reused when large enough (parameter sweeps).
     ChebState &st = sys->cheb;
     st.active = false;
-    st.kernel = kernel == BDG_KERNEL_AUTO ? BDG_KERNEL_DMMA : kernel;
+    st.kernel = kernel;
     st.n_cols = n_cols;
     st.panel_width = n_cols >= 5 ? 8 : (n_cols >= 3 ? 4 : n_cols);
     st.n_panels = (int)ceil_div(n_cols, st.panel_width);
@@ -543,14 +478,20 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
 
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
     // walks one contiguous range of block rows (neighbouring rows share their X records in L1).
-    int per_sm = 1;
-    BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(st.kernel, st.panel_width, false, sys->packed_max_row), kThreads, 0));
-    per_sm = std::max(per_sm, 1);
-    const int64_t target = (int64_t)sys->sm_count * per_sm;
-    int64_t gx = std::max<int64_t>(1, target / st.n_panels);
-    const int rows_per_warp_pass = st.kernel == BDG_KERNEL_FMA ? kWarps * (32 / st.panel_width) : kWarps;
-    gx = std::min<int64_t>(gx, ceil_div(n, rows_per_warp_pass));
-    st.grid_x = (int)gx;
+    if (st.kernel == BDG_KERNEL_ELL) {
+        BDG_TRY(ell_configure(sys));
+    } else {
+        int per_sm = 1;
+        BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(st.kernel, st.panel_width, false, sys->packed_max_row), kThreads, 0));
+        per_sm = std::max(per_sm, 1);
+        const int64_t target = (int64_t)sys->sm_count * per_sm;
+        int64_t gx = std::max<int64_t>(1, target / st.n_panels);
+        const int rows_per_warp_pass = st.kernel == BDG_KERNEL_FMA ? kWarps * (32 / st.panel_width) : kWarps;
+        gx = std::min<int64_t>(gx, ceil_div(n, rows_per_warp_pass));
+        st.grid_x = (int)gx;
+        st.panels_per_group = 1;
+        st.n_groups = st.n_panels;
+    }
 
     const size_t vec_elems = (size_t)st.n_panels * n * st.panel_width * 4;
     BDG_TRY(dev_alloc(sys, st.vec[0], vec_elems * sizeof(double2)));

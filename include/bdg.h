@@ -102,10 +102,14 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
  *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
-/* DMMA = FP64 warp-MMA formulation (default), FMA = scalar formulation; SIMPLE / CHUNKED are the
- * unpipelined MMA kernel with wavefront / per-CTA-chunk row traversal (tuning references). */
-enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_DMMA_SIMPLE = 4,
-       BDG_KERNEL_DMMA_CHUNKED = 5 };
+/* AUTO = ELL when the matrix qualifies, else DMMA.
+ * ELL  = FP64 warp-MMA on the kernel-native fixed-width row format (block rows of <= 8 blocks: every
+ *        lattice Hamiltonian), one pass over the matrix serving up to 32 columns;
+ * DMMA = FP64 warp-MMA on the BSR arrays as exported (any row length);
+ * FMA  = scalar formulation (A/B reference); SIMPLE / CHUNKED = unpipelined DMMA with wavefront /
+ *        per-CTA-chunk row traversal (tuning references). */
+enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_ELL = 3,
+       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5 };
 
 /* Start a recursion on n_cols start vectors resident on this GPU.
  *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)

@@ -6,8 +6,8 @@ import numpy as np
 import bodge_b200 as b
 from bodge_b200 import workloads
 
-PEAK = 6459.3
-def run(cfg, k, kernels=("dmma", "dmma_simple", "fma"), steps=50):
+PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+def run(cfg, k, kernels=("ell", "dmma"), steps=50):
     c = workloads.CONFIGS[cfg]
     t0 = time.time()
     packed = c["build"](c["shape"])
@@ -31,5 +31,7 @@ def run(cfg, k, kernels=("dmma", "dmma_simple", "fma"), steps=50):
         s.cheb_end()
 
 if __name__ == "__main__":
-    for cfg, k in [("C5", 8), ("C4", 8), ("C2", 256), ("C3", 512), ("C5", 1), ("C5", 4), ("C5", 16)]:
-        run(cfg, k)
+    sel = sys.argv[1:] or ["C5:8", "C4:8", "C2:256", "C3:512", "C5:1", "C5:4", "C5:16", "C5:32", "C5:64", "C4:64"]
+    for item in sel:
+        cfg, k = item.split(":")
+        run(cfg, int(k))

@@ -25,7 +25,7 @@ def random_system(gpu_api):
     return cases.random_periodic(gpu_api, (3, 5, 7), seed=11)
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+@pytest.mark.parametrize("kernel", ["ell", "dmma", "fma"])
 @pytest.mark.parametrize("n_cols", [1, 2, 3, 4, 5, 8, 12, 19])
 def test_random_column_moments(random_system, kernel, n_cols):
     system = random_system
@@ -40,7 +40,7 @@ def test_random_column_moments(random_system, kernel, n_cols):
     assert rel_err(summed, want.sum(axis=1)) <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+@pytest.mark.parametrize("kernel", ["ell", "dmma", "fma"])
 def test_probe_moments_match_fixture(gpu_api, observables, kernel):
     """Fixture = scipy recursion on the REFERENCE's own matrix("bsr")."""
     builders = {"readme_12_12_1": lambda: cases.readme_swave(gpu_api, (12, 12, 1)),
@@ -57,7 +57,7 @@ def test_probe_moments_match_fixture(gpu_api, observables, kernel):
         assert rel_err(random, want[:, 4:]) <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "fma"])
+@pytest.mark.parametrize("kernel", ["ell", "dmma", "fma"])
 def test_recursion_vectors(random_system, kernel):
     """The vectors themselves after a few steps: T_n and T_{n-1} against the scipy recursion."""
     system = random_system
@@ -215,3 +215,84 @@ def test_full_size_chebyshev_properties(gpu_api):
     H = small.matrix("bsr")
     want = orc.cheb_moments(H, orc.rademacher(1234, H.shape[0], np.arange(8)), 32, small.spectral_bound())
     assert rel_err(small.chebyshev_moments(32, vectors=8, seed=1234), want) <= TOL
+
+
+# ---- the fixed-width (ELL) step kernel: format edge cases ------------------------------------
+def _moments_vs_oracle(system, n_cols, kernel, n_moments=48, seed=7):
+    H = scipy_of(system)
+    scale = system.spectral_bound()
+    want = orc.cheb_moments(H, orc.rademacher(seed, H.shape[0], np.arange(n_cols)), n_moments, scale)
+    got = system.chebyshev_moments(n_moments, vectors=n_cols, seed=seed, scale=scale, kernel=kernel)
+    return rel_err(got, want)
+
+
+def test_ell_rows_without_diagonal_block(gpu_api):
+    """Pure hopping model: no H[i,i], no Δ[i,i] -> eliminate_zeros drops every diagonal block and
+    slot 0 of every ELL row is padding; T_n[row] must still be found."""
+    lattice = gpu_api.CubicLattice((6, 5, 1))
+    system = gpu_api.Hamiltonian(lattice)
+    with system as (H, D):
+        for i, j in lattice.bonds():
+            H[i, j] = -1.0 * gpu_api.σ0 + 0.3j * (j[0] - i[0] + j[1] - i[1]) * gpu_api.σ3
+            if i[0] < 3:
+                D[i, j] = 0.2 * gpu_api.jσ2
+                D[j, i] = 0.2 * gpu_api.jσ2
+    ex = system.matrix("bsr")
+    assert not any(r in ex.indices[ex.indptr[r] : ex.indptr[r + 1]] for r in range(lattice.size))
+    for kernel in ("ell", "dmma"):
+        assert _moments_vs_oracle(system, 5, kernel) <= TOL
+    # mixed: some rows with, some without a diagonal block
+    with system as (H, D):
+        for i in lattice.sites():
+            if (i[0] + i[1]) % 3 == 0:
+                H[i, i] = 0.7 * gpu_api.σ0 + 0.1 * gpu_api.σ1
+    assert _moments_vs_oracle(system, 9, "ell") <= TOL
+
+
+@pytest.mark.parametrize("n_cols", [16, 17, 24, 33, 40, 70])
+def test_ell_many_columns_share_one_matrix_pass(random_system, n_cols):
+    """k > 8: panels are processed in groups of up to four per pass over the matrix, the last
+    group ragged (n_panels = 2, 3, 3, 5, 5, 9)."""
+    assert _moments_vs_oracle(random_system, n_cols, "ell") <= TOL
+    a = random_system.chebyshev_moments(20, vectors=n_cols, seed=3, kernel="ell")
+    b = random_system.chebyshev_moments(20, vectors=n_cols, seed=3, kernel="dmma")
+    assert rel_err(a, b) <= 1e-12
+    # per-column results do not depend on which panel/group a column lands in
+    c = random_system.chebyshev_moments(20, vectors=n_cols, seed=3, kernel="ell", batch=8)
+    assert rel_err(c, a) <= 1e-13
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 1, 1), (2, 2, 2), (4, 4, 1), (3, 3, 3)])
+def test_ell_row_widths(gpu_api, shape):
+    """Row widths 1 (padded to 3), 3, 4, 5 and 7."""
+    system = cases.random_periodic(gpu_api, shape, seed=5)
+    assert _moments_vs_oracle(system, 3, "ell") <= TOL
+    assert _moments_vs_oracle(system, 11, "ell") <= TOL
+
+
+def test_long_rows_fall_back_to_the_generic_kernel(gpu_api):
+    """A lattice whose rows exceed 8 blocks cannot use the fixed-width format: auto picks the
+    BSR kernel, and asking for kernel='ell' explicitly is an error."""
+    import bodge_b200 as b
+
+    class Dense1D(b.CubicLattice):
+        """Chain with bonds to the 1st..5th neighbours (11 blocks per interior row)."""
+
+        def bonds(self, axis=None):
+            for x in range(self.shape[0]):
+                for d in range(1, 6):
+                    if x + d < self.shape[0]:
+                        yield (x, 0, 0), (x + d, 0, 0)
+                        yield (x + d, 0, 0), (x, 0, 0)
+
+    lattice = Dense1D((40, 1, 1))
+    system = b.Hamiltonian(lattice)
+    with system as (H, D):
+        for i in lattice.sites():
+            H[i, i] = 0.3 * b.σ0
+            D[i, i] = 0.1 * b.jσ2
+        for i, j in lattice.bonds():
+            H[i, j] = -(1.0 / abs(j[0] - i[0])) * b.σ0
+    assert _moments_vs_oracle(system, 6, "auto") <= TOL
+    with pytest.raises(ValueError):
+        system.chebyshev_moments(8, vectors=2, kernel="ell")
