@@ -297,7 +297,7 @@ def run_ours(args):
     achieved = bytes_step * K / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(f"{args.config}_k{cols}"), "peak_source": peak_src,
-                "kernel": "cheb_step_dmma", "algorithmic_bytes_per_launch": bytes_step,
+                "kernel": "cheb_step_ell" if args.kernel in ("auto", "ell") else "cheb_step_" + args.kernel, "algorithmic_bytes_per_launch": bytes_step,
                 "kernel_ms_per_launch": kernel_ms / K}
 
     cpu = None

@@ -79,6 +79,7 @@ struct ChebState {
     DevBuf mu_tmp;    // staging for moment read-out
     int grid_x = 0;
     int panels_per_group = 1;  // ELL kernel: panels sharing one pass over the matrix (grid.y = groups)
+    int panel_batch = 1;       // ... of which this many have their loads in flight together
     int n_groups = 0;
     int64_t launches = 0;
 };

@@ -21,6 +21,7 @@
 // store -- about half the L1 wavefronts of the interleaved-complex formulation in cheb.cu, which
 // ncu showed to be the co-limiter next to HBM (l1tex data-pipe wavefronts 77 % at 1.9 GHz).
 #include <algorithm>
+#include <cstdlib>
 
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
@@ -43,14 +44,14 @@ __device__ __forceinline__ double ld_block(const double *p, uint64_t policy) {
     return v;
 }
 
-template <int PW, int CH, int NP>
+template <int PW, int CH, int NP, int PB>
 __global__ void __launch_bounds__(kThreads, 4)
 cheb_step_ell(const int32_t *__restrict__ cidx, const double *__restrict__ cdata, const double2 *__restrict__ x_cur,
               double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha, double beta, int first,
               int stream_matrix, double *__restrict__ partials, unsigned *__restrict__ tickets,
               double *__restrict__ dots_step) {
     constexpr int REC = PW * 4;           // complex elements per site record
-    constexpr int PB = NP >= 2 ? 2 : 1;   // panels whose loads are in flight together
+    static_assert(NP % PB == 0, "PB = panels whose loads are in flight together");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int panel0 = blockIdx.y * NP;
     const size_t plane = (size_t)n_sites * REC;
@@ -180,27 +181,33 @@ ell_fill(int n_sites, int width, const int32_t *__restrict__ indptr, const int32
 using EllKernel = void (*)(const int32_t *, const double *, const double2 *, double2 *, int, int, double, double, int,
                            int, double *, unsigned *, double *);
 
-template <int PW, int NP> EllKernel pick_ch(int width) {
+template <int PW, int NP, int PB> EllKernel pick_ch(int width) {
     switch (width) {
-        case 3: return cheb_step_ell<PW, 3, NP>;
-        case 4: return cheb_step_ell<PW, 4, NP>;
-        case 5: return cheb_step_ell<PW, 5, NP>;
-        case 6: return cheb_step_ell<PW, 6, NP>;
-        case 7: return cheb_step_ell<PW, 7, NP>;
-        default: return cheb_step_ell<PW, 8, NP>;
+        case 3: return cheb_step_ell<PW, 3, NP, PB>;
+        case 4: return cheb_step_ell<PW, 4, NP, PB>;
+        case 5: return cheb_step_ell<PW, 5, NP, PB>;
+        case 6: return cheb_step_ell<PW, 6, NP, PB>;
+        case 7: return cheb_step_ell<PW, 7, NP, PB>;
+        default: return cheb_step_ell<PW, 8, NP, PB>;
     }
 }
 
-EllKernel pick_ell(int pw, int np, int width) {
+EllKernel pick_ell(int pw, int np, int pb, int width) {
     switch (pw) {
-        case 1: return pick_ch<1, 1>(width);
-        case 2: return pick_ch<2, 1>(width);
-        case 4: return pick_ch<4, 1>(width);
+        case 1: return pick_ch<1, 1, 1>(width);
+        case 2: return pick_ch<2, 1, 1>(width);
+        case 4: return pick_ch<4, 1, 1>(width);
         default:
-            if (np >= 4) return pick_ch<8, 4>(width);
-            if (np >= 2) return pick_ch<8, 2>(width);
-            return pick_ch<8, 1>(width);
+            if (np >= 8) return pick_ch<8, 8, 1>(width);
+            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2>(width) : pick_ch<8, 4, 1>(width);
+            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2>(width) : pick_ch<8, 2, 1>(width);
+            return pick_ch<8, 1, 1>(width);
     }
+}
+
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
 }
 
 }  // namespace
@@ -252,11 +259,25 @@ int ell_build(bdg_system *sys) {
 int ell_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    st.panels_per_group = st.panel_width == 8 ? (st.n_panels >= 3 ? 4 : st.n_panels) : 1;
+    // Measured (profiles/r01/sweep_ell_v1.log): these kernels are latency-bound once the vectors
+    // dominate, so occupancy (24 warps/SM at one panel per warp-row) beats reusing the block
+    // registers for 4 or 8 panels (16 warps/SM) -- concurrent panel groups sweep the lattice in
+    // step and L2 de-duplicates their matrix reads.  Two panels per pass pay off when the matrix
+    // is L2-resident or the rows are long (3-D lattices: more block bytes per record byte).
+    const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;
+    const bool pair = st.panel_width == 8 && st.n_panels >= 2 && (e.width >= 6 || matrix_bytes < ((size_t)64 << 20));
+    st.panels_per_group = pair ? 2 : 1;
+    st.panel_batch = st.panels_per_group;
+    // tuning overrides (development): BDG_ELL_NP in {1,2,4,8}, BDG_ELL_PB in {1,2}
+    if (st.panel_width == 8) {
+        st.panels_per_group = std::min(env_int("BDG_ELL_NP", st.panels_per_group), std::max(st.n_panels, 1));
+        st.panels_per_group = st.panels_per_group >= 8 ? 8 : st.panels_per_group >= 4 ? 4 : st.panels_per_group >= 2 ? 2 : 1;
+        st.panel_batch = st.panels_per_group >= 8 ? 1 : std::min(env_int("BDG_ELL_PB", st.panel_batch), st.panels_per_group);
+    }
     st.n_groups = (int)ceil_div(st.n_panels, st.panels_per_group);
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, pick_ell(st.panel_width, st.panels_per_group, e.width), kThreads, 0));
+        &per_sm, pick_ell(st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads, 0));
     per_sm = std::max(per_sm, 1);
     int64_t gx = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_groups);
     gx = std::min<int64_t>(gx, ceil_div(e.n_sites, kWarps));
@@ -267,7 +288,7 @@ int ell_configure(bdg_system *sys) {
 int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    EllKernel k = pick_ell(st.panel_width, st.panels_per_group, e.width);
+    EllKernel k = pick_ell(st.panel_width, st.panels_per_group, st.panel_batch, e.width);
     // Stream the matrix through L2 (evict-first) only when nothing will read it again soon: one
     // group per pass and a matrix that cannot stay resident in the 126 MB L2 anyway.
     const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;

@@ -7,7 +7,7 @@ import bodge_b200 as b
 from bodge_b200 import workloads
 
 PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
-def run(cfg, k, kernels=("ell", "dmma"), steps=50):
+def run(cfg, k, kernels=tuple(os.environ.get("QP_KERNELS", "ell,dmma").split(",")), steps=50):
     c = workloads.CONFIGS[cfg]
     t0 = time.time()
     packed = c["build"](c["shape"])
@@ -25,7 +25,7 @@ def run(cfg, k, kernels=("ell", "dmma"), steps=50):
         ms = s.cheb_steps(steps, timed=True)
         info = s.cheb_info()
         gbs = info["bytes_per_step"] * steps / (ms * 1e-3) / 1e9
-        print(json.dumps(dict(cfg=cfg, k=k, kernel=kernel, ms_per_step=ms / steps, steps_per_s=steps / (ms * 1e-3),
+        print(json.dumps(dict(cfg=cfg, k=k, kernel=kernel, np=os.environ.get("BDG_ELL_NP"), pb=os.environ.get("BDG_ELL_PB"), ms_per_step=ms / steps, steps_per_s=steps / (ms * 1e-3),
                               GBps=gbs, frac=gbs / PEAK, nb=info["n_blocks"], panels=info["n_panels"], pw=info["panel_width"],
                               host_gen_s=t1 - t0, skeleton_s=t2 - t1, fill_s=t3 - t2)), flush=True)
         s.cheb_end()
