@@ -55,6 +55,8 @@ SIGNATURES = {
     "bdg_cheb_vectors": [_vp, C.c_int, _vp],
     "bdg_cheb_info": [_vp, _i64p, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64p],
     "bdg_cheb_end": [_vp],
+    "bdg_kpm_resolvent": [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int],
+    "bdg_kpm_contract": [_vp, C.c_int32, _vp, C.c_int, _vp, C.c_int],
 }
 
 _lib = None
@@ -269,3 +271,20 @@ class System:
 
     def cheb_end(self):
         check(load().bdg_cheb_end(self._h))
+
+    # -- observables evaluated on the device from the current recursion's moments -----------------
+    def kpm_resolvent(self, n_moments: int, n_cols: int, w, pref) -> np.ndarray:
+        """``g[c, e] = pref[e] * sum_n (2 - δ_n0) mu_n[c] w[e]**n`` as complex ``[n_cols, len(w)]``."""
+        w, pref = _as(w, np.complex128), _as(pref, np.complex128)
+        if w.shape != pref.shape or w.ndim != 1:
+            raise ValueError("w and pref must be 1-D arrays of equal length")
+        out = np.empty((n_cols, len(w)), dtype=np.complex128)
+        check(load().bdg_kpm_resolvent(self._h, int(n_moments), len(w), _ptr(w), _ptr(pref), _ptr(out), 0))
+        return out
+
+    def kpm_contract(self, coef, n_cols: int, summed: bool = False):
+        """``sum_n coef[n] mu_n[c]`` per column (``[n_cols]``) or summed over the columns (float)."""
+        coef = _as(coef, np.float64)
+        out = np.empty(1 if summed else n_cols, dtype=np.float64)
+        check(load().bdg_kpm_contract(self._h, len(coef), _ptr(coef), int(summed), _ptr(out), 0))
+        return float(out[0]) if summed else out

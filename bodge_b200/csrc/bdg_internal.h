@@ -77,6 +77,7 @@ struct ChebState {
     DevBuf partials;  // per-CTA partial dot products of the step in flight
     DevBuf tickets;   // uint32 [n_panels] arrival counters (last CTA reduces)
     DevBuf mu_tmp;    // staging for moment read-out
+    DevBuf obs_tmp;   // staging for observables.cu (coefficients, energies, results)
     int grid_x = 0;
     int panels_per_group = 1;  // ELL kernel: panels sharing one pass over the matrix (grid.y = groups)
     int panel_batch = 1;       // ... of which this many have their loads in flight together

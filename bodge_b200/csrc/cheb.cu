@@ -433,6 +433,7 @@ void cheb_release(bdg_system *sys) {
     dev_free(sys, st.partials);
     dev_free(sys, st.tickets);
     dev_free(sys, st.mu_tmp);
+    dev_free(sys, st.obs_tmp);
     ell_release(sys);
     const int64_t launches = st.launches;
     st = ChebState();

@@ -197,6 +197,15 @@ class Hamiltonian:
         the columns are split over the ranks (each holds a replica of the matrix) and combined
         with one all-reduce / all-gather; every rank gets the full result.
         """
+        return self._columns(moments, lambda sysn, k: sysn.cheb_read(moments, k, summed=summed), summed,
+                             rows=rows, vectors=vectors, seed=seed, scale=scale, kernel=kernel, batch=batch, group=group)
+
+    def _columns(self, moments, read, summed, *, rows=None, vectors=None, seed=1234, scale=None, kernel="auto",
+                 batch=None, group="auto"):
+        """Run the recursion for ``moments`` moments over all start columns -- sharded over the
+        ranks of the process group, in batches on this GPU -- and reduce each batch ON THE DEVICE
+        with ``read(system, n_columns)``, which returns ``[m, n_columns]`` (per column) or ``[m]``
+        (``summed``).  One collective combines the ranks."""
         if (rows is None) == (vectors is None):
             raise ValueError("give either rows= (probe columns) or vectors= (random columns)")
         scale = self.spectral_bound() if scale is None else float(scale)
@@ -204,20 +213,11 @@ class Hamiltonian:
         rows = None if rows is None else np.asarray(rows, dtype=np.int64)
         rank, world, group = distributed.resolve(group)
         lo, hi = distributed.shard_range(n_total, rank, world)
-
-        def local():
-            return self._local_moments(moments, rows, lo, hi, seed, scale, summed, kernel, batch)
-
-        return distributed.combine(local(), summed, n_total, rank, world, group, device=self.device)
-
-    def _local_moments(self, moments, rows, lo, hi, seed, scale, summed, kernel, batch):
         n_local = hi - lo
-        out = np.zeros(moments) if summed else np.zeros((moments, n_local))
-        if n_local == 0:
-            return out
         if batch is None:  # two vector sets of 64*N*k bytes each; keep them under ~16 GB
             batch = max(8, int(8e9 // (64 * self.lattice.size)) // 8 * 8)
         steps = (moments + 1) // 2 - 1
+        parts = []
         for b0 in range(0, n_local, batch):
             b1 = min(n_local, b0 + batch)
             if rows is not None:
@@ -225,12 +225,19 @@ class Hamiltonian:
             else:
                 self._sys.cheb_begin(n_random=b1 - b0, seed=seed, col_offset=lo + b0, scale=scale, kernel=kernel)
             self._sys.cheb_steps(steps)
-            mu = self._sys.cheb_read(moments, b1 - b0, summed=summed)
-            if summed:
-                out += mu
-            else:
-                out[:, b0:b1] = mu
-        return out
+            parts.append(np.asarray(read(self._sys, b1 - b0), dtype=np.float64))
+        if summed:
+            local = np.sum(parts, axis=0) if parts else None
+        else:
+            local = np.concatenate(parts, axis=1) if parts else None
+        if local is None:  # this rank got no columns: learn the leading dimension from a dry call shape
+            m = self._leading_dim(read, moments)
+            local = np.zeros(m) if summed else np.zeros((m, 0))
+        return distributed.combine(local, summed, n_total, rank, world, group, device=self.device)
+
+    @staticmethod
+    def _leading_dim(read, moments):
+        return getattr(read, "leading_dim", moments)
 
     # ------------------------------------------------------------------------------------
     # observables
@@ -292,12 +299,19 @@ class Hamiltonian:
 
         scale = self.spectral_bound() if scale is None else float(scale)
         n_mom = kpm.default_moments(T, scale) if moments is None else int(moments)
+        # F = sum_n c_n Tr T_n(H/scale): the series is contracted with the moments on the device,
+        # so one double per GPU crosses PCIe / NVLink instead of the moment arrays.
+        coef = kpm.chebyshev_coefficients(lambda e: kpm.free_energy_density(e, T), n_mom, scale)
+
+        def read(sysn, k):
+            return np.array([sysn.kpm_contract(coef, k, summed=True)])
+
+        read.leading_dim = 1
         if vectors is None:
-            mu = self.chebyshev_moments(n_mom, rows=np.arange(self.shape[0]), scale=scale, summed=True, kernel=kernel)
-        else:
-            mu = self.chebyshev_moments(n_mom, vectors=vectors, seed=seed, scale=scale, summed=True, kernel=kernel)
-            mu = mu / vectors
-        return kpm.free_energy_from_trace(mu, T, scale)
+            total = self._columns(n_mom, read, True, rows=np.arange(self.shape[0]), scale=scale, kernel=kernel)
+            return float(total[0])
+        total = self._columns(n_mom, read, True, vectors=vectors, seed=seed, scale=scale, kernel=kernel)
+        return float(total[0]) / vectors
 
     @typecheck
     def ldos(self, site: Coord, energies: Matrix | list[float], *, moments: int | None = None,
@@ -321,5 +335,17 @@ class Hamiltonian:
             raise ValueError("need at least two distinct |energies| to define the broadening Γ")
         if moments is None:
             moments = kpm.ldos_moments_needed(scale, float(np.min(np.abs(np.gradient(eps)))))
-        mu = self.chebyshev_moments(int(moments), rows=self._probe_rows(sites), scale=scale, kernel=kernel)
-        return np.stack([kpm.ldos_from_site_moments(mu[:, 4 * s : 4 * s + 4], energies, scale) for s in range(len(sites))])
+        moments = int(moments)
+        # Resolvent diagonal at z = (ε + iΓ)/scale for every probe column and energy, evaluated on
+        # the device from the moments (csrc/observables.cu); only [n_columns, n_energies] comes back.
+        w, pref = kpm.resolvent_weights((eps + 1j * np.gradient(eps)) / scale)
+        pref = pref / scale
+
+        def read(sysn, k):
+            g = sysn.kpm_resolvent(moments, k, w, pref)             # complex [k, n_eps]
+            return np.concatenate([g.real.T, g.imag.T], axis=0)     # [2 n_eps, k]: columns last for the gather
+
+        read.leading_dim = 2 * len(eps)
+        out = self._columns(moments, read, False, rows=self._probe_rows(sites), scale=scale, kernel=kernel)
+        g_imag = out[len(eps):].T.reshape(len(sites), 4, len(eps))  # Im G[site, α, ε]
+        return kpm.ldos_from_resolvent(g_imag, eps, energies)

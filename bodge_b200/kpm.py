@@ -76,6 +76,29 @@ def resolvent_diagonal(mu, z: complex) -> complex:
     return (-1j / np.sin(t)) * acc
 
 
+def resolvent_weights(z):
+    """Per-energy constants of the resolvent series, vectorised over ``z``: ``w = exp(-i t)`` with
+    ``t = arccos z`` on the branch where ``|w| < 1`` and the prefactor ``-i / sin t``, so that
+    ``<x|(z - H~)^-1|x> = pref * sum_n (2 - delta_n0) mu_n w**n`` (the device kernel's inputs)."""
+    z = np.asarray(z, dtype=np.complex128)
+    t = np.arccos(z)
+    t = np.where(np.abs(np.exp(-1j * t)) > 1, -t, t)
+    return np.exp(-1j * t), -1j / np.sin(t)
+
+
+def ldos_from_resolvent(g_imag, eps, energies) -> np.ndarray:
+    """LDOS ``[site, energy]`` from ``Im <e_{4i+α}|(ε + iΓ - H)^-1|e_{4i+α}>`` given as
+    ``g_imag[site, α, ε]`` for the sorted distinct ``eps = unique(|energies|)``: electrons
+    (α = 0, 1) at ``+ε``, holes (α = 2, 3) at ``-ε`` (bodge/hamiltonian.py:376-382)."""
+    energies = np.array(energies, dtype=float)
+    pos = np.searchsorted(eps, np.abs(energies))
+    electron = -(g_imag[:, 0, :] + g_imag[:, 1, :]) / math.pi
+    hole = -(g_imag[:, 2, :] + g_imag[:, 3, :]) / math.pi
+    # the reference fills ρ[+ε] then ρ[-ε] into one dict, so ε = 0 (being -0.0 == +0.0) ends up with the hole value
+    use_electron = energies > 0
+    return np.where(use_electron[None, :], electron[:, pos], hole[:, pos])
+
+
 def ldos_moments_needed(scale: float, gamma_min: float, tol: float = 1e-13, cap: int = 1 << 20) -> int:
     """The resolvent series is geometric with ratio ``|exp(-i t)| ~ 1 - Γ/scale``."""
     n = int(math.ceil(-math.log(tol) * scale / gamma_min))

@@ -142,6 +142,18 @@ int bdg_cheb_info(bdg_t *sys, int64_t *n_blocks, int64_t *bytes_per_step, int32_
                   int32_t *n_panels, int64_t *launches);
 int bdg_cheb_end(bdg_t *sys);
 
+/* ---- observables from the moments of the current recursion, evaluated on the device ----------
+ *      (consumers: ldos() bodge/hamiltonian.py:349-382, free_energy() bodge/hamiltonian.py:305-319) */
+/* g[c * n_z + e] = pref[e] * sum_{n < n_moments} (2 - delta_n0) mu_n[c] w[e]^n   (complex, interleaved).
+ * With w = exp(-i arccos z), |w| < 1, and pref = -i / sin(arccos z) this is the resolvent diagonal
+ * <x_c| (z - H/scale)^-1 |x_c>: all energies of an LDOS curve for all probe columns in one launch. */
+int bdg_kpm_resolvent(bdg_t *sys, int32_t n_moments, int32_t n_z, const double *w, const double *pref,
+                      double *g, int g_on_device);
+/* out[c] = sum_n coef[n] mu_n[c]  (BDG_MU_PER_COLUMN) or the sum of that over this GPU's columns
+ * (BDG_MU_SUM, one double): e.g. coef = Chebyshev coefficients of the free-energy density. */
+int bdg_kpm_contract(bdg_t *sys, int32_t n_moments, const double *coef, int reduce, double *out,
+                     int out_on_device);
+
 #ifdef __cplusplus
 }
 #endif

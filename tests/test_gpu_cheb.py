@@ -296,3 +296,68 @@ def test_long_rows_fall_back_to_the_generic_kernel(gpu_api):
     assert _moments_vs_oracle(system, 6, "auto") <= TOL
     with pytest.raises(ValueError):
         system.chebyshev_moments(8, vectors=2, kernel="ell")
+
+
+# ---- observables evaluated on the device (csrc/observables.cu) -------------------------------
+def test_device_resolvent_and_contraction(random_system):
+    from bodge_b200 import kpm
+
+    system = random_system
+    n_mom, k = 300, 11
+    scale = system.spectral_bound()
+    mu = system.chebyshev_moments(n_mom, vectors=k, seed=21, scale=scale)
+    sysn = system._sys
+    sysn.cheb_begin(n_random=k, seed=21, scale=scale)
+    sysn.cheb_steps(n_mom // 2 - 1)
+    # resolvent diagonal at a few complex energies, both half planes
+    z = np.array([0.1 + 0.05j, -0.4 + 0.02j, 0.0 + 0.1j, 0.7 - 0.03j])
+    w, pref = kpm.resolvent_weights(z)
+    got = sysn.kpm_resolvent(n_mom, k, w, pref)
+    want = np.array([[kpm.resolvent_diagonal(mu[:, c], zz) for zz in z] for c in range(k)])
+    assert got.shape == (k, len(z))
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    # series contraction
+    coef = np.cos(0.37 * np.arange(n_mom)) / (1 + np.arange(n_mom))
+    per_col = sysn.kpm_contract(coef, k)
+    assert np.allclose(per_col, coef @ mu, rtol=1e-12, atol=1e-12)
+    total = sysn.kpm_contract(coef, k, summed=True)
+    assert abs(total - float(coef @ mu.sum(axis=1))) <= 1e-12 * abs(total)
+    # fewer moments than available, odd count
+    per_col = sysn.kpm_contract(coef[:77], k)
+    assert np.allclose(per_col, coef[:77] @ mu[:77], rtol=1e-12, atol=1e-12)
+    sysn.cheb_end()
+
+
+def test_ldos_map_many_sites_matches_single_site_calls(gpu_api):
+    system = cases.dwave_rashba(gpu_api, (9, 8, 1))
+    sites = [(x, y, 0) for x in range(0, 9, 2) for y in range(0, 8, 3)]
+    E = np.linspace(-0.4, 0.4, 9)
+    many = system.ldos_map(sites, E, moments=600)
+    assert many.shape == (len(sites), len(E))
+    for s in (0, 7, len(sites) - 1):
+        one = system.ldos(sites[s], E, moments=600)
+        assert np.allclose(many[s], one, rtol=1e-12, atol=1e-14)
+    assert (many >= 0).all()
+
+
+def test_full_size_ldos_map_C3(gpu_api):
+    """C3 (100x100 d-wave + Rashba): LDOS at the 1024 probe sites of SURVEY 8d (4096 probe
+    columns in one batch), size-independent checks only."""
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    shape = (100, 100, 1)
+    system = b.Hamiltonian(b.CubicLattice(shape))
+    system.fill(*workloads.dwave_rashba(shape))
+    sites = [(3 * p + 2, 3 * q + 2, 0) for p in range(32) for q in range(32)]
+    E = np.linspace(-0.15, 0.15, 11)
+    rho = system.ldos_map(sites, E, moments=768)
+    assert rho.shape == (1024, 11) and np.isfinite(rho).all() and (rho >= 0).all()
+    # a probe's result does not depend on which other columns share its batch / panel
+    pick = [0, 517, 1023]
+    alone = system.ldos_map([sites[i] for i in pick], E, moments=768)
+    assert np.allclose(rho[pick], alone, rtol=1e-11, atol=1e-14)
+    # bulk sites related by the lattice's C4 symmetry about the centre see the same LDOS ... up to
+    # the finite-size asymmetry of the probe grid; the d-wave gap suppresses the LDOS at ε = 0
+    bulk = rho[[i for i, s in enumerate(sites) if 30 <= s[0] < 70 and 30 <= s[1] < 70]]
+    assert bulk[:, 5].mean() < 0.8 * bulk[:, 0].mean()

@@ -123,3 +123,26 @@ def test_shard_range():
     assert distributed.resolve("auto")[:2] == (0, 1)
     local = np.arange(6.0).reshape(3, 2)
     assert distributed.combine(local, False, 2, 0, 1) is local
+
+
+def test_vectorised_resolvent_path_equals_per_energy_path():
+    """ldos_from_resolvent(resolvent_weights(...)) -- the host half of the device LDOS path --
+    against ldos_from_site_moments (per-energy Horner), incl. ε = 0 and unsorted/duplicate energies."""
+    from bodge_b200 import kpm
+
+    rng = np.random.default_rng(3)
+    lam = rng.uniform(-0.9, 0.9, size=40)                 # spectrum of a fake H~
+    wts = rng.random((4, 40))
+    wts /= wts.sum(axis=1, keepdims=True)
+    n = 3000
+    mu4 = np.stack([(wts[a][None, :] * np.cos(np.arange(n)[:, None] * np.arccos(lam)[None, :])).sum(axis=1) for a in range(4)], axis=1)
+    scale = 2.5
+    energies = np.array([0.3, -0.3, 0.0, 0.7, -0.1, 0.1, 0.7])
+    want = kpm.ldos_from_site_moments(mu4, energies, scale)
+    eps = np.unique(np.abs(energies))
+    w, pref = kpm.resolvent_weights((eps + 1j * np.gradient(eps)) / scale)
+    m = 2.0 * mu4
+    m[0] = mu4[0]
+    g = np.stack([[(pref[e] / scale) * np.polyval(m[::-1, a], w[e]) for e in range(len(eps))] for a in range(4)])
+    got = kpm.ldos_from_resolvent(g.imag[None], eps, energies)[0]
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-13)
