@@ -20,7 +20,9 @@ OK, E_INVALID, E_CUDA, E_NOT_NEIGHBOUR, E_NOT_HERMITIAN, E_OUT_OF_BOUNDS, E_NO_D
 X0_PROBE, X0_RADEMACHER = 0, 1
 MU_PER_COLUMN, MU_SUM = 0, 1
 KERNEL_AUTO, KERNEL_DMMA, KERNEL_FMA = 0, 1, 2
-KERNELS = {"auto": KERNEL_AUTO, "dmma": KERNEL_DMMA, "fma": KERNEL_FMA, "ell": 3, "dmma_simple": 4, "dmma_chunked": 5}
+KERNELS = {"auto": KERNEL_AUTO, "dmma": KERNEL_DMMA, "fma": KERNEL_FMA, "ell": 3, "dmma_simple": 4, "dmma_chunked": 5,
+           "dict": 6}
+KERNEL_NAMES = {v: k for k, v in KERNELS.items()}
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -54,6 +56,7 @@ SIGNATURES = {
     "bdg_cheb_moments": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int32, C.c_int, _vp, C.c_int],
     "bdg_cheb_vectors": [_vp, C.c_int, _vp],
     "bdg_cheb_info": [_vp, _i64p, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64p],
+    "bdg_cheb_format": [_vp, C.POINTER(C.c_int32), _i64p, _i64p],
     "bdg_cheb_end": [_vp],
     "bdg_kpm_resolvent": [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int],
     "bdg_kpm_contract": [_vp, C.c_int32, _vp, C.c_int, _vp, C.c_int],
@@ -261,6 +264,12 @@ class System:
         out = np.empty((4 * self.n_sites, n_cols), dtype=np.complex128)
         check(load().bdg_cheb_vectors(self._h, int(which), _ptr(out)))
         return out
+
+    def cheb_format(self) -> dict:
+        """Kernel / matrix format the active recursion runs on (``kernel="auto"`` resolved)."""
+        k, mb, nu = C.c_int32(), C.c_int64(), C.c_int64()
+        check(load().bdg_cheb_format(self._h, C.byref(k), C.byref(mb), C.byref(nu)))
+        return {"kernel": KERNEL_NAMES[k.value], "matrix_bytes_per_step": mb.value, "distinct_blocks": nu.value}
 
     def cheb_info(self) -> dict:
         nb, by, la = C.c_int64(), C.c_int64(), C.c_int64()

@@ -511,6 +511,9 @@ extern "C" int bdg_create_cubic(int device, int32_t Lx, int32_t Ly, int32_t Lz, 
     BDG_REQUIRE(n64 * 7 < INT32_MAX, "lattice too large for int32 BSR indices");
     bdg_system *sys = nullptr;
     BDG_TRY(create_common(device, &sys));
+    sys->cubic[0] = Lx;
+    sys->cubic[1] = Ly;
+    sys->cubic[2] = Lz;
     const int n = (int)n64;
     int rc = [&]() -> int {
         BDG_TRY(dev_alloc(sys, sys->skel.indptr, (size_t)(n + 1) * sizeof(int32_t)));

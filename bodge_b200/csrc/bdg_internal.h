@@ -59,6 +59,21 @@ struct BsrDev {
     DevBuf data;     // double2 [n_blocks * 16]
 };
 
+// Row traversal of the fixed-width step kernels (cheb_ell.cu).  The lattice is cut into work
+// items = (patch of Pz x Py sites in the z-y plane, one site per warp of the CTA) x (segment of
+// `seg_len` consecutive x); a CTA marches its patch along x, so the +-x neighbour records of a row
+// are the records the same warp touched one and two steps earlier, and the +-y / +-z neighbours
+// belong to the warps next to it: they are served by the SM's L1, not by L2.  Items are handed
+// out segment-major (item = it * gridDim.x + blockIdx.x), so the grid still sweeps the lattice as
+// one wavefront and every vector byte leaves HBM once.  Matrices without cubic geometry use the
+// degenerate walk Lz = n_sites, Pz = warps per CTA, Lx = 1 (plain wavefront over consecutive rows).
+struct RowWalk {
+    int Lz = 1, Ly = 1, Lx = 1;  // extents (site = z + y*Lz + x*Ly*Lz)
+    int Pz = 1, Py = 1;          // patch extents; Pz * Py = warps per CTA
+    int nPz = 1, n_patches = 1;  // patches along z, patches in the plane
+    int seg_len = 1, n_items = 1;
+};
+
 // ---- Chebyshev state ----------------------------------------------------------------------
 struct ChebState {
     bool active = false;
@@ -82,6 +97,7 @@ struct ChebState {
     int panels_per_group = 1;  // ELL kernel: panels sharing one pass over the matrix (grid.y = groups)
     int panel_batch = 1;       // ... of which this many have their loads in flight together
     int n_groups = 0;
+    RowWalk walk;              // ELL / DICT kernels: row traversal
     int64_t launches = 0;
 };
 
@@ -96,6 +112,12 @@ struct EllDev {
     int width = 0;
     int64_t n_sites = 0;
     DevBuf idx, data;
+    // Block dictionary over the same slots (cheb_ell.cu, DICT kernels): the DISTINCT blocks of the
+    // matrix, and one code per slot.  Usable when the distinct blocks are a small fraction of all.
+    //   code  int32  [n_sites][width]          table double [n_unique][4][2][4]
+    bool dict_usable = false;
+    int64_t n_unique = 0;
+    DevBuf code, table;
 };
 
 struct bdg_system {
@@ -104,6 +126,7 @@ struct bdg_system {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int64_t dev_bytes = 0;
+    int cubic[3] = {0, 0, 0};  // (Lx, Ly, Lz) when built by bdg_create_cubic, else zeros
 
     BsrDev skel;           // full skeleton, values as scattered so far
     BsrDev packed;         // after eliminate_zeros (built lazily)

@@ -380,7 +380,7 @@ int launch_step(bdg_system *sys, bool first) {
     double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
     const double2 *x_cur = st.vec[st.cur].as<double2>();
     double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
-    if (st.kernel == BDG_KERNEL_ELL) {
+    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT) {
         BDG_TRY(ell_launch_step(sys, first, x_cur, x_io, dots_step));
         st.cur ^= 1;
         st.launches += 1;
@@ -451,13 +451,16 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DMMA_CHUNKED, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DICT, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
-    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL) {
+    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT) {
         BDG_TRY(ell_build(sys));
-        BDG_REQUIRE(kernel == BDG_KERNEL_AUTO || sys->ell.usable,
+        BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
                     "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");
-        kernel = sys->ell.usable ? BDG_KERNEL_ELL : BDG_KERNEL_DMMA;
+        BDG_REQUIRE(kernel != BDG_KERNEL_DICT || sys->ell.dict_usable,
+                    "the block-dictionary kernel needs a fixed-width matrix whose distinct blocks are few");
+        if (kernel == BDG_KERNEL_AUTO)
+            kernel = sys->ell.dict_usable ? BDG_KERNEL_DICT : sys->ell.usable ? BDG_KERNEL_ELL : BDG_KERNEL_DMMA;
     }
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;
@@ -479,7 +482,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
 
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
     // walks one contiguous range of block rows (neighbouring rows share their X records in L1).
-    if (st.kernel == BDG_KERNEL_ELL) {
+    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT) {
         BDG_TRY(ell_configure(sys));
     } else {
         int per_sm = 1;
@@ -627,6 +630,25 @@ extern "C" int bdg_cheb_info(bdg_t *sys, int64_t *n_blocks, int64_t *bytes_per_s
     if (panel_width) *panel_width = st.panel_width;
     if (n_panels) *n_panels = st.n_panels;
     if (launches) *launches = st.launches;
+    return BDG_OK;
+}
+
+extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_bytes_per_step, int64_t *n_distinct_blocks) {
+    BDG_ENTER(sys);
+    const ChebState &st = sys->cheb;
+    BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
+    const BsrDev &m = sys->packed;
+    const EllDev &e = sys->ell;
+    if (kernel) *kernel = st.kernel;
+    if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
+    if (matrix_bytes_per_step) {
+        if (st.kernel == BDG_KERNEL_DICT)
+            *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
+        else if (st.kernel == BDG_KERNEL_ELL)
+            *matrix_bytes_per_step = e.n_sites * e.width * 260;
+        else
+            *matrix_bytes_per_step = 260 * m.n_blocks + 4 * (m.n_sites + 1);
+    }
     return BDG_OK;
 }
 

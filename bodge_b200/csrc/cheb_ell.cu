@@ -44,12 +44,27 @@ __device__ __forceinline__ double ld_block(const double *p, uint64_t policy) {
     return v;
 }
 
-template <int PW, int CH, int NP, int PB>
+// Table blocks (DICT): a few KB..MB re-read by every row that changes its block pattern -- keep in L1/L2.
+// Predicated (not branched) so that the row body stays ONE basic block: ptxas schedules per block,
+// and a block boundary between the loads and the MMAs lets it issue an MMA -- and stall on its
+// operands -- before the last loads of the row have been issued.
+__device__ __forceinline__ void ld_table_if(double &v, const double *p, unsigned take) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.f64 %0, [%1];\n}\n"
+                 : "+d"(v)
+                 : "l"(p), "r"(take));
+}
+
+// DICT = block-dictionary matrix format: `cdata` is the table of DISTINCT blocks (B-fragment order)
+// and `ccode[row][slot]` names the table entry of every slot.  The B fragments stay in registers
+// from one row of the warp to the next and a slot is re-fetched only when its code changes
+// (warp-uniform test), so on a lattice with a few distinct hopping / on-site terms the matrix
+// costs 8 bytes per block of HBM traffic instead of 260 and no L1 wavefronts at all.
+template <int PW, int CH, int NP, int PB, bool DICT>
 __global__ void __launch_bounds__(kThreads, 4)
-cheb_step_ell(const int32_t *__restrict__ cidx, const double *__restrict__ cdata, const double2 *__restrict__ x_cur,
-              double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha, double beta, int first,
-              int stream_matrix, double *__restrict__ partials, unsigned *__restrict__ tickets,
-              double *__restrict__ dots_step) {
+cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode, const double *__restrict__ cdata,
+              const double2 *__restrict__ x_cur, double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha,
+              double beta, int first, int stream_matrix, double *__restrict__ partials,
+              unsigned *__restrict__ tickets, double *__restrict__ dots_step, const RowWalk wk) {
     constexpr int REC = PW * 4;           // complex elements per site record
     static_assert(NP % PB == 0, "PB = panels whose loads are in flight together");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,28 +73,68 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const double *__restrict__ cdata
     const bool x_lane = lane < REC;       // lanes past the record (PW < 8) compute on element 0 and discard
     const int x_elem = x_lane ? lane : 0;
     const uint64_t policy = l2_policy(stream_matrix != 0);
-    // Wavefront traversal (see cheb.cu): in pass t the grid works on rows (t*gridDim.x + b)*kWarps + w.
-    const int stride = gridDim.x * kWarps;
+    // Per-row index fetch: lanes 0..CH-1 read the slot's block column, lanes 8..8+CH-1 its code (DICT).
+    const int32_t *islot = (DICT && lane >= 8) ? ccode - 8 : cidx;
+    const bool ilane = DICT ? ((lane & 7) < CH && lane < 16) : lane < CH;
 
-    int row = blockIdx.x * kWarps + warp;
+    // Row traversal (RowWalk, bdg_internal.h): this warp owns one site of the CTA's patch and
+    // marches it along x through the item's segment; `row` is the row in hand, `nrow` the one after.
+    const int M = wk.Lz * wk.Ly;
+    int item = (int)blockIdx.x - (int)gridDim.x, row = -1, row_end = 0;
+    auto next_row = [&](int r) -> int {
+        if (wk.Lx == 1 && wk.Ly == 1) {  // consecutive rows, one per warp and item
+            item += gridDim.x;
+            r = item * wk.Pz + warp;
+            return item < wk.n_items && r < wk.Lz ? r : -1;
+        }
+        r += M;
+        while (r >= row_end || r < 0) {
+            item += gridDim.x;
+            if (item >= wk.n_items) return -1;
+            const int seg = item / wk.n_patches, p = item - seg * wk.n_patches;
+            const int py = p / wk.nPz, pz = p - py * wk.nPz;
+            const int z = pz * wk.Pz + warp % wk.Pz, y = py * wk.Py + warp / wk.Pz;
+            if (z >= wk.Lz || y >= wk.Ly) continue;  // ragged patch: this warp has no site in it
+            const int x0 = seg * wk.seg_len, x1 = min(wk.Lx, x0 + wk.seg_len);
+            r = z + y * wk.Lz + x0 * M;
+            row_end = z + y * wk.Lz + (x1 - 1) * M + 1;
+        }
+        return r;
+    };
+    row = next_row(-1 - M);
+    int nrow = row >= 0 ? next_row(row) : -1;
     int jv = 0;
-    if (row < n_sites && lane < CH) jv = __ldg(cidx + (size_t)row * CH + lane);
+    if (row >= 0 && ilane) jv = __ldg(islot + (size_t)row * CH + lane);
 
     double d0[NP], d1[NP];
 #pragma unroll
     for (int pp = 0; pp < NP; ++pp) d0[pp] = d1[pp] = 0.0;
+    double keep[DICT ? CH : 1];  // DICT: B fragments carried from row to row
+#pragma unroll
+    for (int u = 0; u < (DICT ? CH : 1); ++u) keep[u] = 0.0;
+    int jheld = -1;              // DICT: lanes 8.. remember the code of the fragment held for their slot
 
-    for (; row < n_sites; row += stride) {
+    for (; row >= 0; row = nrow, nrow = row >= 0 ? next_row(row) : -1) {
         int jn[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) jn[u] = __shfl_sync(kFull, jv, u);
         double bop[CH];
-        const double *blk = cdata + (size_t)row * CH * 32 + lane;
+        if (DICT) {
+            const unsigned changed = __ballot_sync(kFull, jv != jheld) >> 8;  // warp-uniform
+            jheld = jv;
 #pragma unroll
-        for (int u = 0; u < CH; ++u) bop[u] = ld_block(blk + u * 32, policy);
-        const int nrow = row + stride;
+            for (int u = 0; u < CH; ++u) {
+                const int code = __shfl_sync(kFull, jv, 8 + u);
+                ld_table_if(keep[u], cdata + (size_t)code * 32 + lane, changed >> u & 1u);
+                bop[u] = keep[u];
+            }
+        } else {
+            const double *blk = cdata + (size_t)row * CH * 32 + lane;
+#pragma unroll
+            for (int u = 0; u < CH; ++u) bop[u] = ld_block(blk + u * 32, policy);
+        }
         int jnext = 0;
-        if (nrow < n_sites && lane < CH) jnext = __ldg(cidx + (size_t)nrow * CH + lane);
+        if (nrow >= 0 && ilane) jnext = __ldg(islot + (size_t)nrow * CH + lane);
         const size_t off = (size_t)row * REC + x_elem;
 
 #pragma unroll
@@ -178,31 +233,94 @@ ell_fill(int n_sites, int width, const int32_t *__restrict__ indptr, const int32
     if (lane == 0) cidx[w] = src >= 0 ? indices[p0 + src] : row;
 }
 
-using EllKernel = void (*)(const int32_t *, const double *, const double2 *, double2 *, int, int, double, double, int,
-                           int, double *, unsigned *, double *);
+// ---- block dictionary ---------------------------------------------------------------------------
+// Distinct blocks are found with an open-addressing hash table keyed by a 64-bit hash of the
+// block's 256 bytes; every slot is then compared bit for bit with its table entry, so a hash
+// collision can only disable the format, never change a result.
+constexpr unsigned long long kEmptyKey = ~0ull;
 
-template <int PW, int NP, int PB> EllKernel pick_ch(int width) {
+// One warp per slot: hash, find-or-insert, remember the table position and the smallest slot id
+// holding that key (the representative whose bytes become the table entry).
+__global__ void __launch_bounds__(256)
+dict_insert(int64_t n_slots, const double *__restrict__ cdata, unsigned long long *__restrict__ keys,
+            int *__restrict__ rep, unsigned cap_mask, int32_t *__restrict__ where) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_slots) return;
+    const uint64_t bits = (uint64_t)__double_as_longlong(cdata[w * 32 + lane]);
+    uint64_t h = mix64(bits + 0x9E3779B97F4A7C15ull * (uint64_t)(lane + 1));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    h = mix64(h);
+    if (h == kEmptyKey) h = 0x1234567ull;
+    if (lane != 0) return;
+    unsigned pos = (unsigned)h & cap_mask;
+    for (;;) {
+        unsigned long long seen = *((volatile unsigned long long *)(keys + pos));  // cheap hit for repeated blocks
+        if (seen == kEmptyKey) seen = atomicCAS(keys + pos, kEmptyKey, (unsigned long long)h);
+        if (seen == kEmptyKey || seen == h) break;
+        pos = (pos + 1) & cap_mask;
+    }
+    if (*((volatile int *)(rep + pos)) > (int)w) atomicMin(rep + pos, (int)w);
+    where[w] = (int32_t)pos;
+}
+
+__global__ void __launch_bounds__(256)
+dict_flag_used(int64_t cap, const unsigned long long *__restrict__ keys, int32_t *__restrict__ used) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cap) used[t] = keys[t] != kEmptyKey;
+}
+
+// One warp per slot: code = dense id of its table position; the representative writes the table
+// entry; everyone else is compared with the representative's bytes.
+__global__ void __launch_bounds__(256)
+dict_emit(int64_t n_slots, const double *__restrict__ cdata, const int *__restrict__ rep,
+          const int32_t *__restrict__ dense, const int32_t *__restrict__ where, int32_t *__restrict__ ccode,
+          double *__restrict__ table, int table_cap, int *__restrict__ mismatch) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_slots) return;
+    const int pos = where[w];
+    const int code = dense[pos];
+    const int r = rep[pos];
+    const long long mine = __double_as_longlong(cdata[w * 32 + lane]);
+    if (r == (int)w) {
+        if (code < table_cap) table[(size_t)code * 32 + lane] = __longlong_as_double(mine);
+    } else if (mine != __double_as_longlong(cdata[(int64_t)r * 32 + lane])) {
+        *mismatch = 1;
+    }
+    if (lane == 0) ccode[w] = code;
+}
+
+using EllKernel = void (*)(const int32_t *, const int32_t *, const double *, const double2 *, double2 *, int, int,
+                           double, double, int, int, double *, unsigned *, double *, const RowWalk);
+
+template <int PW, int NP, int PB, bool DICT> EllKernel pick_ch(int width) {
     switch (width) {
-        case 3: return cheb_step_ell<PW, 3, NP, PB>;
-        case 4: return cheb_step_ell<PW, 4, NP, PB>;
-        case 5: return cheb_step_ell<PW, 5, NP, PB>;
-        case 6: return cheb_step_ell<PW, 6, NP, PB>;
-        case 7: return cheb_step_ell<PW, 7, NP, PB>;
-        default: return cheb_step_ell<PW, 8, NP, PB>;
+        case 3: return cheb_step_ell<PW, 3, NP, PB, DICT>;
+        case 4: return cheb_step_ell<PW, 4, NP, PB, DICT>;
+        case 5: return cheb_step_ell<PW, 5, NP, PB, DICT>;
+        case 6: return cheb_step_ell<PW, 6, NP, PB, DICT>;
+        case 7: return cheb_step_ell<PW, 7, NP, PB, DICT>;
+        default: return cheb_step_ell<PW, 8, NP, PB, DICT>;
     }
 }
 
-EllKernel pick_ell(int pw, int np, int pb, int width) {
+template <bool DICT> EllKernel pick_shape(int pw, int np, int pb, int width) {
     switch (pw) {
-        case 1: return pick_ch<1, 1, 1>(width);
-        case 2: return pick_ch<2, 1, 1>(width);
-        case 4: return pick_ch<4, 1, 1>(width);
+        case 1: return pick_ch<1, 1, 1, DICT>(width);
+        case 2: return pick_ch<2, 1, 1, DICT>(width);
+        case 4: return pick_ch<4, 1, 1, DICT>(width);
         default:
-            if (np >= 8) return pick_ch<8, 8, 1>(width);
-            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2>(width) : pick_ch<8, 4, 1>(width);
-            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2>(width) : pick_ch<8, 2, 1>(width);
-            return pick_ch<8, 1, 1>(width);
+            if (np >= 8) return pick_ch<8, 8, 1, DICT>(width);
+            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2, DICT>(width) : pick_ch<8, 4, 1, DICT>(width);
+            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2, DICT>(width) : pick_ch<8, 2, 1, DICT>(width);
+            return pick_ch<8, 1, 1, DICT>(width);
     }
+}
+
+EllKernel pick_ell(bool dict, int pw, int np, int pb, int width) {
+    return dict ? pick_shape<true>(pw, np, pb, width) : pick_shape<false>(pw, np, pb, width);
 }
 
 int env_int(const char *name, int fallback) {
@@ -210,11 +328,132 @@ int env_int(const char *name, int fallback) {
     return v && *v ? atoi(v) : fallback;
 }
 
+// Plan the row traversal for `slots` resident CTAs per panel group (RowWalk, bdg_internal.h).
+RowWalk plan_walk(const bdg_system *sys, int n_sites, int64_t slots) {
+    RowWalk w;
+    const int Lx = sys->cubic[0], Ly = sys->cubic[1], Lz = sys->cubic[2];
+    const bool cubic = (int64_t)Lx * Ly * Lz == n_sites && n_sites > 0;
+    if (!cubic || Ly * Lz < 2 * kWarps || Lx < 8 || env_int("BDG_ELL_WALK", 1) == 0) {
+        // consecutive rows, one per warp: the wavefront sweep of cheb.cu
+        w.Lz = std::max(n_sites, 1);
+        w.Pz = kWarps;
+        w.nPz = (int)ceil_div(w.Lz, kWarps);
+        w.n_patches = w.n_items = w.nPz;
+        return w;
+    }
+    w.Lx = Lx, w.Ly = Ly, w.Lz = Lz;
+    w.Pz = Lz == 1 ? 1 : (Ly == 1 ? kWarps : 2);
+    w.Pz = std::max(1, std::min(env_int("BDG_ELL_PZ", w.Pz), kWarps));
+    while (kWarps % w.Pz) --w.Pz;
+    w.Py = kWarps / w.Pz;
+    w.nPz = (int)ceil_div(Lz, w.Pz);
+    w.n_patches = w.nPz * (int)ceil_div(Ly, w.Py);
+    // Segment length: long segments amortise the two cold columns at the start of an item, many
+    // items balance the CTAs.  Score = (share of CTA slots doing useful work) x (1 - cold share).
+    double best = -1.0;
+    const int forced = env_int("BDG_ELL_SEG", 0);
+    for (int n_seg = 1; n_seg <= std::max(1, Lx / 8); ++n_seg) {
+        const int len = forced > 0 ? forced : (int)ceil_div(Lx, n_seg);
+        const int64_t items = (int64_t)w.n_patches * ceil_div(Lx, len);
+        const double balance = (double)items / (double)(ceil_div(items, slots) * slots);
+        const double score = balance * len / (len + 2.0);
+        if (score > best) {
+            best = score;
+            w.seg_len = len;
+            w.n_items = (int)items;
+        }
+        if (forced > 0) break;
+    }
+    return w;
+}
+
+// Build the block dictionary of the fixed-width matrix copy (e.idx / e.data must exist).
+int dict_build(bdg_system *sys) {
+    EllDev &e = sys->ell;
+    e.dict_usable = false;
+    e.n_unique = 0;
+    const int64_t n_slots = e.n_sites * e.width;
+    if (n_slots <= 0 || n_slots > (int64_t)1 << 30) return BDG_OK;
+    int64_t cap = 1024;
+    while (cap < 2 * n_slots) cap <<= 1;
+    DevBuf keys, rep, where, dense;
+    int rc = BDG_OK;
+    auto cleanup = [&]() {
+        dev_free(sys, keys);
+        dev_free(sys, rep);
+        dev_free(sys, where);
+        dev_free(sys, dense);
+    };
+#define DICT_TRY(expr)            \
+    do {                          \
+        rc = (expr);              \
+        if (rc != BDG_OK) {       \
+            cleanup();            \
+            return rc;            \
+        }                         \
+    } while (0)
+#define DICT_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t err__ = (expr);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            bdg_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                  \
+                          cudaGetErrorString(err__));                                            \
+            cleanup();                                                                           \
+            return BDG_E_CUDA;                                                                   \
+        }                                                                                        \
+    } while (0)
+    DICT_TRY(dev_alloc(sys, keys, (size_t)cap * sizeof(unsigned long long)));
+    DICT_TRY(dev_alloc(sys, rep, (size_t)cap * sizeof(int)));
+    DICT_TRY(dev_alloc(sys, where, (size_t)n_slots * sizeof(int32_t)));
+    DICT_TRY(dev_alloc(sys, dense, (size_t)(cap + 1) * sizeof(int32_t)));
+    DICT_TRY(ensure_scratch(sys, 2, 64));
+    int *scal = sys->scratch_i32[2].as<int>();  // [0] = number of distinct blocks, [1] = mismatch flag
+    DICT_CUDA(cudaMemsetAsync(keys.ptr, 0xff, (size_t)cap * sizeof(unsigned long long), sys->stream));
+    DICT_CUDA(cudaMemsetAsync(rep.ptr, 0x7f, (size_t)cap * sizeof(int), sys->stream));
+    DICT_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(int), sys->stream));
+    const unsigned warps_grid = (unsigned)ceil_div(n_slots * 32, 256);
+    dict_insert<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), keys.as<unsigned long long>(),
+                                                     rep.as<int>(), (unsigned)(cap - 1), where.as<int32_t>());
+    dict_flag_used<<<(unsigned)ceil_div(cap, 256), 256, 0, sys->stream>>>(cap, keys.as<unsigned long long>(),
+                                                                          dense.as<int32_t>());
+    DICT_CUDA(cudaGetLastError());
+    DICT_TRY(exclusive_scan_i32(sys, dense.as<int32_t>(), dense.as<int32_t>(), cap, scal));
+    int n_unique = 0;
+    DICT_CUDA(cudaMemcpyAsync(&n_unique, scal, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+    DICT_CUDA(cudaStreamSynchronize(sys->stream));
+    e.n_unique = n_unique;
+    // Worth it when the table is a small fraction of the matrix (each distinct block is still
+    // read from HBM about once per step; the codes cost 4 bytes per slot).
+    const int max_frac = env_int("BDG_DICT_MAX_PERCENT", 35);
+    if ((int64_t)n_unique * 100 <= n_slots * max_frac) {
+        DICT_TRY(dev_alloc(sys, e.code, (size_t)n_slots * sizeof(int32_t)));
+        DICT_TRY(dev_alloc(sys, e.table, (size_t)n_unique * 32 * sizeof(double)));
+        dict_emit<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), rep.as<int>(), dense.as<int32_t>(),
+                                                       where.as<int32_t>(), e.code.as<int32_t>(), e.table.as<double>(),
+                                                       n_unique, scal + 1);
+        DICT_CUDA(cudaGetLastError());
+        int mismatch = 0;
+        DICT_CUDA(cudaMemcpyAsync(&mismatch, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+        DICT_CUDA(cudaStreamSynchronize(sys->stream));
+        e.dict_usable = mismatch == 0;
+    }
+    if (!e.dict_usable) {
+        dev_free(sys, e.code);
+        dev_free(sys, e.table);
+    }
+    cleanup();
+#undef DICT_TRY
+#undef DICT_CUDA
+    return BDG_OK;
+}
+
 }  // namespace
 
 void ell_release(bdg_system *sys) {
     dev_free(sys, sys->ell.idx);
     dev_free(sys, sys->ell.data);
+    dev_free(sys, sys->ell.code);
+    dev_free(sys, sys->ell.table);
     sys->ell = EllDev();
 }
 
@@ -225,6 +464,8 @@ int ell_build(bdg_system *sys) {
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;
     e.usable = false;
+    e.dict_usable = false;
+    e.n_unique = 0;
     e.n_sites = n;
     if (n > 0) {
         BDG_TRY(ensure_scratch(sys, 2, 64));
@@ -249,6 +490,7 @@ int ell_build(bdg_system *sys) {
                 e.data.as<double>());
             BDG_CUDA(cudaGetLastError());
             e.usable = true;
+            BDG_TRY(dict_build(sys));
         }
     }
     e.valid = true;
@@ -259,13 +501,15 @@ int ell_build(bdg_system *sys) {
 int ell_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
+    const bool dict = st.kernel == BDG_KERNEL_DICT;
     // Measured (profiles/r01/sweep_ell_v1.log): these kernels are latency-bound once the vectors
     // dominate, so occupancy (24 warps/SM at one panel per warp-row) beats reusing the block
     // registers for 4 or 8 panels (16 warps/SM) -- concurrent panel groups sweep the lattice in
     // step and L2 de-duplicates their matrix reads.  Two panels per pass pay off when the matrix
     // is L2-resident or the rows are long (3-D lattices: more block bytes per record byte).
     const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;
-    const bool pair = st.panel_width == 8 && st.n_panels >= 2 && (e.width >= 6 || matrix_bytes < ((size_t)64 << 20));
+    const bool pair = st.panel_width == 8 && st.n_panels >= 2 &&
+                      (e.width >= 6 || matrix_bytes < ((size_t)64 << 20));
     st.panels_per_group = pair ? 2 : 1;
     st.panel_batch = st.panels_per_group;
     // tuning overrides (development): BDG_ELL_NP in {1,2,4,8}, BDG_ELL_PB in {1,2}
@@ -277,27 +521,33 @@ int ell_configure(bdg_system *sys) {
     st.n_groups = (int)ceil_div(st.n_panels, st.panels_per_group);
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, pick_ell(st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads, 0));
+        &per_sm, pick_ell(dict, st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads,
+        (size_t)env_int("BDG_ELL_PAD", 0)));
     per_sm = std::max(per_sm, 1);
-    int64_t gx = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_groups);
-    gx = std::min<int64_t>(gx, ceil_div(e.n_sites, kWarps));
-    st.grid_x = (int)gx;
+    const int64_t slots = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_groups);
+    st.walk = plan_walk(sys, (int)e.n_sites, slots);
+    st.grid_x = (int)std::min<int64_t>(slots, st.walk.n_items);
     return BDG_OK;
 }
 
 int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    EllKernel k = pick_ell(st.panel_width, st.panels_per_group, st.panel_batch, e.width);
+    const bool dict = st.kernel == BDG_KERNEL_DICT;
+    EllKernel k = pick_ell(dict, st.panel_width, st.panels_per_group, st.panel_batch, e.width);
     // Stream the matrix through L2 (evict-first) only when nothing will read it again soon: one
     // group per pass and a matrix that cannot stay resident in the 126 MB L2 anyway.
     const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;
     const int stream_matrix = st.n_groups == 1 && matrix_bytes > (size_t)64 << 20;
     dim3 grid((unsigned)st.grid_x, (unsigned)st.n_groups);
-    k<<<grid, kThreads, 0, sys->stream>>>(e.idx.as<int32_t>(), e.data.as<double>(), static_cast<const double2 *>(x_cur),
-                                          static_cast<double2 *>(x_io), (int)e.n_sites, st.n_panels,
-                                          (first ? 1.0 : 2.0) / st.scale, first ? 0.0 : 1.0, first ? 1 : 0,
-                                          stream_matrix, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step);
+    const size_t pad = (size_t)env_int("BDG_ELL_PAD", 0);  // occupancy experiments: unused dynamic shared memory
+    if (pad > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    k<<<grid, kThreads, pad, sys->stream>>>(e.idx.as<int32_t>(), dict ? e.code.as<int32_t>() : nullptr,
+                                          dict ? e.table.as<double>() : e.data.as<double>(),
+                                          static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_io),
+                                          (int)e.n_sites, st.n_panels, (first ? 1.0 : 2.0) / st.scale, first ? 0.0 : 1.0,
+                                          first ? 1 : 0, stream_matrix, st.partials.as<double>(),
+                                          st.tickets.as<unsigned>(), dots_step, st.walk);
     BDG_CUDA(cudaGetLastError());
     return BDG_OK;
 }

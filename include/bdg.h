@@ -102,14 +102,19 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
  *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
-/* AUTO = ELL when the matrix qualifies, else DMMA.
+/* AUTO = DICT when the matrix qualifies, else ELL when it qualifies, else DMMA.
+ * DICT = the ELL kernel on a block-dictionary copy of the matrix: the distinct 4x4 blocks once, plus a
+ *        4-byte code per block.  Lattice Hamiltonians repeat a handful of hopping / on-site blocks
+ *        millions of times, so the per-step matrix traffic drops from 260 to 8 bytes per block; the
+ *        arithmetic and its order are those of ELL (results are bit-identical).  Chosen when the
+ *        distinct blocks are <= 35 % of all blocks;
  * ELL  = FP64 warp-MMA on the kernel-native fixed-width row format (block rows of <= 8 blocks: every
  *        lattice Hamiltonian), one pass over the matrix serving up to 32 columns;
  * DMMA = FP64 warp-MMA on the BSR arrays as exported (any row length);
  * FMA  = scalar formulation (A/B reference); SIMPLE / CHUNKED = unpipelined DMMA with wavefront /
  *        per-CTA-chunk row traversal (tuning references). */
 enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_ELL = 3,
-       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5 };
+       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6 };
 
 /* Start a recursion on n_cols start vectors resident on this GPU.
  *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)
@@ -140,6 +145,10 @@ int bdg_cheb_vectors(bdg_t *sys, int which /*0 = T_n, 1 = T_{n-1}*/, double *out
  * number of blocks after eliminate_zeros. */
 int bdg_cheb_info(bdg_t *sys, int64_t *n_blocks, int64_t *bytes_per_step, int32_t *panel_width,
                   int32_t *n_panels, int64_t *launches);
+/* What the current recursion actually runs on: *kernel = the BDG_KERNEL_* in use (AUTO resolved),
+ * *matrix_bytes_per_step = bytes of matrix data one step reads in that format (blocks or table +
+ * codes + indices), *n_distinct_blocks = size of the block dictionary (0 if none was built). */
+int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_bytes_per_step, int64_t *n_distinct_blocks);
 int bdg_cheb_end(bdg_t *sys);
 
 /* ---- observables from the moments of the current recursion, evaluated on the device ----------

@@ -361,3 +361,88 @@ def test_full_size_ldos_map_C3(gpu_api):
     # the finite-size asymmetry of the probe grid; the d-wave gap suppresses the LDOS at ε = 0
     bulk = rho[[i for i, s in enumerate(sites) if 30 <= s[0] < 70 and 30 <= s[1] < 70]]
     assert bulk[:, 5].mean() < 0.8 * bulk[:, 0].mean()
+
+
+# ---- block-dictionary matrix format (kernel="dict") ---------------------------------------------
+def _disordered(api, shape, seed=5):
+    """Uniform hopping, site-dependent on-site potential and gap: every diagonal block distinct."""
+    lattice = api.CubicLattice(shape)
+    system = api.Hamiltonian(lattice)
+    rng = np.random.default_rng(seed)
+    with system as (H, D):
+        for i in lattice.sites():
+            H[i, i] = rng.normal() * api.σ0 + 0.3 * rng.normal() * api.σ3
+            D[i, i] = -0.1 * rng.random() * api.jσ2
+        for i, j in lattice.bonds():
+            H[i, j] = -1.0 * api.σ0
+    return system
+
+
+DICT_SYSTEMS = {
+    "readme_12_12_1": lambda api: cases.readme_swave(api, (12, 12, 1)),
+    "junction_30_10_1": lambda api: cases.junction(api, (30, 10, 1)),
+    "dwave_9_8_1": lambda api: cases.dwave_rashba(api, (9, 8, 1)),
+    "swave3d_6_5_4": lambda api: cases.swave_3d(api, (6, 5, 4)),
+    "chain_17_1_1": lambda api: cases.readme_swave(api, (17, 1, 1)),
+    "disordered_11_9_1": lambda api: _disordered(api, (11, 9, 1)),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(DICT_SYSTEMS))
+def test_dictionary_format_is_bit_identical_to_ell(gpu_api, tag):
+    """Same arithmetic in the same order on a de-duplicated copy of the blocks: not 1e-10, equal."""
+    system = DICT_SYSTEMS[tag](gpu_api)
+    H = scipy_of(system)
+    scale = system.spectral_bound()
+    for n_cols in (1, 3, 8, 19):
+        ell = system.chebyshev_moments(48, vectors=n_cols, seed=3, scale=scale, kernel="ell")
+        dic = system.chebyshev_moments(48, vectors=n_cols, seed=3, scale=scale, kernel="dict")
+        assert np.array_equal(ell, dic)
+        want = orc.cheb_moments(H, orc.rademacher(3, H.shape[0], np.arange(n_cols)), 48, scale)
+        assert rel_err(dic, want) <= TOL
+    sysn = system._sys
+    sysn.cheb_begin(n_random=4, seed=1, scale=scale, kernel="auto")
+    fmt = sysn.cheb_format()
+    assert fmt["kernel"] == "dict"                           # few distinct blocks -> chosen by default
+    n_slots_bytes = 260 * sysn.cheb_info()["n_blocks"]
+    assert fmt["matrix_bytes_per_step"] < n_slots_bytes
+    blocks = {blk.tobytes() for blk in H.data}
+    # distinct stored blocks (+ the zero block used for padding slots / absent diagonals)
+    assert len(blocks) <= fmt["distinct_blocks"] <= len(blocks) + 1
+    sysn.cheb_end()
+
+
+def test_dictionary_format_declines_matrices_without_repetition(random_system):
+    sysn = random_system._sys
+    scale = random_system.spectral_bound()
+    sysn.cheb_begin(n_random=4, seed=1, scale=scale, kernel="auto")
+    fmt = sysn.cheb_format()
+    assert fmt["kernel"] == "ell" and fmt["distinct_blocks"] > 0.9 * sysn.cheb_info()["n_blocks"]
+    with pytest.raises(ValueError):
+        sysn.cheb_begin(n_random=4, seed=1, scale=scale, kernel="dict")
+    sysn.cheb_end()
+
+
+def test_dictionary_format_with_every_block_distinct(gpu_api, monkeypatch):
+    """Forced on a random matrix (table as large as the matrix): still exact."""
+    monkeypatch.setenv("BDG_DICT_MAX_PERCENT", "100")
+    system = cases.random_periodic(gpu_api, (3, 5, 7), seed=11)
+    H = scipy_of(system)
+    scale = system.spectral_bound()
+    want = orc.cheb_moments(H, orc.rademacher(99, H.shape[0], np.arange(11)), 64, scale)
+    got = system.chebyshev_moments(64, vectors=11, seed=99, scale=scale, kernel="dict")
+    assert rel_err(got, want) <= TOL
+    assert np.array_equal(got, system.chebyshev_moments(64, vectors=11, seed=99, scale=scale, kernel="ell"))
+
+
+def test_dictionary_follows_matrix_updates(gpu_api):
+    """A later `with` block changes blocks: the dictionary must be rebuilt, not reused."""
+    system = cases.readme_swave(gpu_api, (10, 6, 1))
+    scale = 9.0
+    before = system.chebyshev_moments(32, vectors=4, seed=2, scale=scale, kernel="dict")
+    with system as (H, D):
+        H[(3, 2, 0), (3, 2, 0)] = 1.7 * gpu_api.σ0 + 0.2 * gpu_api.σ3
+    after = system.chebyshev_moments(32, vectors=4, seed=2, scale=scale, kernel="dict")
+    want = orc.cheb_moments(scipy_of(system), orc.rademacher(2, system.shape[0], np.arange(4)), 32, scale)
+    assert not np.array_equal(before, after)
+    assert rel_err(after, want) <= TOL
