@@ -46,6 +46,8 @@ SIGNATURES = {
     "bdg_scatter": [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_double, _f64p, _i64p],
     "bdg_clear": [_vp],
     "bdg_export_bsr": [_vp, C.c_int, _i64p, _vp, _vp, _vp],
+    "bdg_export_csr": [_vp, C.c_int, _i64p, _vp, _vp, _vp],
+    "bdg_export_dense": [_vp, _vp],
     "bdg_import_data": [_vp, _vp],
     "bdg_norm_inf": [_vp, _f64p],
     "bdg_cheb_begin": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int],
@@ -214,6 +216,22 @@ class System:
         data = np.empty((nb.value, 4, 4), dtype=np.complex128)
         check(lib.bdg_export_bsr(self._h, int(eliminate_zeros), C.byref(nb), _ptr(indptr), _ptr(indices), _ptr(data)))
         return indptr, indices, data
+
+    def export_csr(self, transpose: bool = False):
+        """(indptr, indices, data) of the CSR (or, transposed, CSC) form without explicit zeros."""
+        lib = load()
+        nnz = C.c_int64()
+        indptr = np.empty(4 * self.n_sites + 1, dtype=np.int32)
+        check(lib.bdg_export_csr(self._h, int(transpose), C.byref(nnz), _ptr(indptr), None, None))
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.complex128)
+        check(lib.bdg_export_csr(self._h, int(transpose), C.byref(nnz), _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def export_dense(self) -> np.ndarray:
+        out = np.empty((4 * self.n_sites, 4 * self.n_sites), dtype=np.complex128)
+        check(load().bdg_export_dense(self._h, _ptr(out)))
+        return out
 
     def import_data(self, data):
         data = _as(data, np.complex128)

@@ -841,6 +841,128 @@ extern "C" int bdg_export_bsr(bdg_t *sys, int eliminate_zeros, int64_t *n_blocks
     return BDG_OK;
 }
 
+// ======================================================================================
+// scalar-level exports: matrix("csr") / matrix("csc") / matrix("dense")
+// (bodge/hamiltonian.py:144-151: tocsr()/tocsc() + eliminate_zeros(), todense())
+// ======================================================================================
+// One thread per scalar row (CSR) or scalar column (CSC) of the 4N x 4N matrix.  Entries come
+// out in ascending order of the other index, explicit zeros (re == 0 and im == 0; -0.0 is zero,
+// NaN is not) are dropped -- what scipy's conversion followed by eliminate_zeros() yields.
+// For CSC the blocks of column j are the transposes of the blocks of row j (the skeleton's
+// structure is symmetric); their values are fetched from block (i, j).
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads) scalar_lines(int n_sites, const int32_t *__restrict__ indptr,
+                                                         const int32_t *__restrict__ indices,
+                                                         const double2 *__restrict__ data, int transpose,
+                                                         int32_t *__restrict__ counts,
+                                                         const int32_t *__restrict__ offsets,
+                                                         int32_t *__restrict__ out_idx, double2 *__restrict__ out_val) {
+    const int line = blockIdx.x * kThreads + threadIdx.x;
+    if (line >= 4 * n_sites) return;
+    const int i = line >> 2, a = line & 3;
+    int n = 0;
+    int at = FILL ? offsets[line] : 0;
+    for (int p = indptr[i]; p < indptr[i + 1]; ++p) {
+        const int j = indices[p];
+        const int q = transpose ? find_block(indptr, indices, j, i) : p;
+        if (q < 0) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 v = data[(size_t)q * 16 + (transpose ? b * 4 + a : a * 4 + b)];
+            if (v.x != 0.0 || v.y != 0.0) {
+                if (FILL) {
+                    out_idx[at] = 4 * j + b;
+                    out_val[at] = v;
+                    ++at;
+                }
+                ++n;
+            }
+        }
+    }
+    if (!FILL) counts[line] = n;
+}
+
+// 16 threads per block: element (a, b) of block (i, j) goes to dense[4i + a][4j + b].
+__global__ void __launch_bounds__(kThreads) dense_scatter(int64_t n_blocks, int n_sites,
+                                                          const int32_t *__restrict__ brow,
+                                                          const int32_t *__restrict__ indices,
+                                                          const double2 *__restrict__ data, double2 *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n_blocks * 16) return;
+    const int64_t p = t >> 4;
+    const int a = (int)(t >> 2) & 3, b = (int)t & 3;
+    // scipy's todense() accumulates into zeros: 0.0 + (-0.0) = +0.0
+    const double2 v = data[t];
+    out[((size_t)4 * brow[p] + a) * ((size_t)4 * n_sites) + (size_t)4 * indices[p] + b] =
+        make_double2(v.x + 0.0, v.y + 0.0);
+}
+
+extern "C" int bdg_export_csr(bdg_t *sys, int transpose, int64_t *nnz, int32_t *indptr, int32_t *indices, double *data) {
+    BDG_ENTER(sys);
+    const BsrDev &m = sys->skel;
+    const int n = (int)m.n_sites;
+    const int64_t lines = 4 * (int64_t)n;
+    Scalars *d = sys->scalars.as<Scalars>();
+    BDG_TRY(ensure_scratch(sys, 0, (size_t)(lines + 1) * sizeof(int32_t)));
+    int32_t *offsets = sys->scratch_i32[0].as<int32_t>();
+    scalar_lines<false><<<grid_for(lines), kThreads, 0, sys->stream>>>(n, m.indptr.as<int32_t>(), m.indices.as<int32_t>(),
+                                                                      m.data.as<double2>(), transpose, offsets, nullptr,
+                                                                      nullptr, nullptr);
+    BDG_CUDA(cudaGetLastError());
+    BDG_TRY(exclusive_scan_i32(sys, offsets, offsets, lines, &d->total));
+    BDG_CUDA(cudaMemcpyAsync(offsets + lines, &d->total, sizeof(int32_t), cudaMemcpyDeviceToDevice, sys->stream));
+    int32_t total = 0;
+    BDG_TRY(read_total(sys, &total));
+    if (nnz) *nnz = total;
+    if (indptr)
+        BDG_CUDA(cudaMemcpyAsync(indptr, offsets, (size_t)(lines + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, sys->stream));
+    if (indices && data && total > 0) {
+        DevBuf idx, val;
+        int rc = dev_alloc(sys, idx, (size_t)total * sizeof(int32_t));
+        if (rc == BDG_OK) rc = dev_alloc(sys, val, (size_t)total * sizeof(double2));
+        cudaError_t err = cudaSuccess;
+        if (rc == BDG_OK) {
+            scalar_lines<true><<<grid_for(lines), kThreads, 0, sys->stream>>>(
+                n, m.indptr.as<int32_t>(), m.indices.as<int32_t>(), m.data.as<double2>(), transpose, nullptr, offsets,
+                idx.as<int32_t>(), val.as<double2>());
+            err = cudaGetLastError();
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync(indices, idx.ptr, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, sys->stream);
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync(data, val.ptr, (size_t)total * sizeof(double2), cudaMemcpyDeviceToHost, sys->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(sys->stream);
+        }
+        dev_free(sys, idx);
+        dev_free(sys, val);
+        BDG_TRY(rc);
+        BDG_CUDA(err);
+    }
+    BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    return BDG_OK;
+}
+
+extern "C" int bdg_export_dense(bdg_t *sys, double *out) {
+    BDG_ENTER(sys);
+    BDG_REQUIRE(out != nullptr, "null output");
+    const BsrDev &m = sys->skel;
+    const size_t side = (size_t)4 * m.n_sites;
+    const size_t bytes = side * side * sizeof(double2);
+    DevBuf dense;
+    BDG_TRY(dev_alloc(sys, dense, bytes));
+    cudaError_t err = cudaMemsetAsync(dense.ptr, 0, bytes, sys->stream);
+    if (err == cudaSuccess && m.n_blocks > 0) {
+        dense_scatter<<<grid_for(m.n_blocks * 16), kThreads, 0, sys->stream>>>(
+            m.n_blocks, (int)m.n_sites, m.brow.as<int32_t>(), m.indices.as<int32_t>(), m.data.as<double2>(),
+            dense.as<double2>());
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out, dense.ptr, bytes, cudaMemcpyDeviceToHost, sys->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(sys->stream);
+    dev_free(sys, dense);
+    BDG_CUDA(err);
+    return BDG_OK;
+}
+
 extern "C" int bdg_norm_inf(bdg_t *sys, double *norm) {
     BDG_ENTER(sys);
     BDG_REQUIRE(norm != nullptr, "null output");

@@ -121,3 +121,62 @@ def ldos_from_site_moments(mu4, energies, scale: float) -> np.ndarray:
         table[+e] = -np.imag(diag[0] + diag[1]) / math.pi
         table[-e] = -np.imag(diag[2] + diag[3]) / math.pi
     return np.array([table[e] for e in energies])
+
+
+# ------------------------------------------------------------------------------------------
+# Spectral bounds from the moments: Lanczos without a Lanczos kernel
+# ------------------------------------------------------------------------------------------
+def jacobi_from_moments(mu) -> tuple[np.ndarray, np.ndarray]:
+    """Lanczos coefficients of ``(H~, x)`` from the Chebyshev moments ``mu_n = <x|T_n(H~)|x>``.
+
+    The moments are the modified moments of the spectral measure of ``x`` with respect to the
+    Chebyshev polynomials, so the modified Chebyshev algorithm (Sack-Donovan / Wheeler; Gautschi,
+    *Orthogonal Polynomials*, 2.1.7) turns ``2m`` of them into the ``m x m`` Jacobi matrix that
+    ``m`` Lanczos steps started at ``x`` would produce -- the GPU recursion that computes the
+    moments IS the Krylov process, no extra kernel or vector pass is needed.  With the measure
+    supported inside [-1, 1] the map is well conditioned.
+
+    Returns ``(alpha[0..m-1], beta[1..m-1])``: diagonal and squared off-diagonal of the matrix.
+    """
+    nu = np.asarray(mu, dtype=np.float64)
+    m = len(nu) // 2
+    if m < 1 or nu[0] <= 0:
+        raise ValueError("need at least two moments of a non-zero vector")
+    # x T_l = a_l T_{l+1} + c_l T_{l-1}:  a_0 = 1, c_0 = 0;  a_l = c_l = 1/2 for l >= 1
+    a = np.full(2 * m, 0.5)
+    a[0] = 1.0
+    c = np.full(2 * m, 0.5)
+    c[0] = 0.0
+    alpha, beta = np.zeros(m), np.zeros(m)
+    alpha[0] = a[0] * nu[1] / nu[0]
+    beta[0] = nu[0]
+    prev2 = np.zeros(2 * m)   # sigma_{k-2, l}
+    prev1 = nu[: 2 * m].copy()  # sigma_{k-1, l}
+    for k in range(1, m):
+        cur = np.zeros(2 * m)
+        ls = np.arange(k, 2 * m - k)
+        cur[ls] = a[ls] * prev1[ls + 1] - alpha[k - 1] * prev1[ls] + c[ls] * prev1[ls - 1] - beta[k - 1] * prev2[ls]
+        if not cur[k] > 0:  # measure exhausted: the Krylov space is invariant after k steps
+            return alpha[:k], beta[1:k]
+        alpha[k] = a[k] * cur[k + 1] / cur[k] - a[k - 1] * prev1[k] / prev1[k - 1]
+        beta[k] = a[k - 1] * cur[k] / prev1[k - 1]
+        prev2, prev1 = prev1, cur
+    return alpha, beta[1:]
+
+
+def spectral_radius_from_moments(mu, scale: float) -> tuple[float, float]:
+    """``(ritz, bound)`` for ``max |eigenvalue of H|`` from moments of ``H / scale``: the largest
+    Ritz value in magnitude and the safeguarded estimate ``ritz + |residual|`` (the Ritz value
+    approaches the spectral edge from inside; the residual of its Ritz vector bounds the distance to
+    the nearest eigenvalue)."""
+    from scipy.linalg import eigh_tridiagonal
+
+    alpha, beta = jacobi_from_moments(mu)
+    m = len(alpha)
+    if m == 1:
+        return abs(alpha[0]) * scale, abs(alpha[0]) * scale
+    # keep the last coefficient as the residual norm of the (m-1)-step factorisation
+    theta, vecs = eigh_tridiagonal(alpha[: m - 1], np.sqrt(beta[: m - 2])) if m > 2 else (alpha[:1], np.ones((1, 1)))
+    k = int(np.argmax(np.abs(theta)))
+    resid = math.sqrt(beta[m - 2]) * abs(vecs[-1, k])
+    return float(abs(theta[k]) * scale), float((abs(theta[k]) + resid) * scale)

@@ -90,6 +90,14 @@ int bdg_clear(bdg_t *sys);
  * block whose 16 entries all compare == 0 (scipy bsr eliminate_zeros), else the full skeleton. */
 int bdg_export_bsr(bdg_t *sys, int eliminate_zeros, int64_t *n_blocks, int32_t *indptr,
                    int32_t *indices, double *data);
+/* Scalar-level exports of the 4N x 4N matrix: replace matrix("csr") / matrix("csc") / matrix("dense")
+ * (bodge/hamiltonian.py:144-151: scipy tocsr()/tocsc() + eliminate_zeros(), todense()).
+ * bdg_export_csr: transpose = 0 gives CSR, 1 gives CSC; int32 indptr[4N+1] and indices[nnz] (ascending
+ * inside every row / column), data[nnz] complex128; explicit zeros are dropped.  Two-phase like
+ * bdg_export_bsr: indices = data = NULL returns *nnz (and indptr if given).
+ * bdg_export_dense: out[4N][4N] complex128, row-major. */
+int bdg_export_csr(bdg_t *sys, int transpose, int64_t *nnz, int32_t *indptr, int32_t *indices, double *data);
+int bdg_export_dense(bdg_t *sys, double *out);
 /* Overwrite all stored values from a host array laid out like the skeleton's data (inverse of
  * export with eliminate_zeros = 0; used for `system._data[...] = ...` style direct edits). */
 int bdg_import_data(bdg_t *sys, const double *data);

@@ -178,6 +178,36 @@ def eliminate_zeros(indptr, indices, data):
     return new_ptr.astype(np.int32), indices[keep].copy(), data[keep].copy()
 
 
+def export_scalar(indptr, indices, data, transpose=False):
+    """``matrix("csr")`` (``transpose=False``) / ``matrix("csc")`` (``transpose=True``):
+    scipy ``tocsr()`` / ``tocsc()`` followed by ``eliminate_zeros()`` (bodge/hamiltonian.py:144-149),
+    restated without scipy: expand the skeleton's blocks to scalar entries, order them by
+    (row, column) or (column, row), drop entries that compare ``== 0``.  int32 indices."""
+    n = len(indptr) - 1
+    brow = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    a = np.arange(4, dtype=np.int64)
+    rows = (4 * brow[:, None, None] + a[None, :, None]) + 0 * a[None, None, :]
+    cols = (4 * indices.astype(np.int64)[:, None, None] + a[None, None, :]) + 0 * a[None, :, None]
+    rows, cols, vals = rows.ravel(), cols.ravel(), np.asarray(data).reshape(-1)
+    keep = vals != 0
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    major, minor = (cols, rows) if transpose else (rows, cols)
+    order = np.lexsort((minor, major))
+    ptr = np.zeros(4 * n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(major, minlength=4 * n), out=ptr[1:])
+    return ptr.astype(np.int32), minor[order].astype(np.int32), vals[order]
+
+
+def export_dense(indptr, indices, data):
+    """``matrix("dense")``: ``todense()`` of the skeleton (bodge/hamiltonian.py:150-151).  scipy ADDS
+    the blocks into a zero matrix, so a stored ``-0.0`` comes out as ``+0.0``."""
+    n = len(indptr) - 1
+    brow = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    out = np.zeros((n, 4, n, 4), dtype=np.complex128)
+    out[brow, :, indices.astype(np.int64), :] = np.asarray(data) + 0.0
+    return out.reshape(4 * n, 4 * n)
+
+
 def to_scipy(indptr, indices, data):
     n = len(indptr) - 1
     return sp.bsr_matrix((data, indices, indptr), shape=(4 * n, 4 * n), blocksize=(4, 4))

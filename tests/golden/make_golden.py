@@ -53,6 +53,17 @@ def struct_of(system):
     )
 
 
+def format_digests(system):
+    """sha256 of what the reference's matrix("csr") / ("csc") / ("dense") return (hamiltonian.py:144-151)."""
+    csr, csc = system.matrix("csr"), system.matrix("csc")
+    assert csr.indptr.dtype == np.int32 and csc.indices.dtype == np.int32
+    return dict(
+        csr_structure=digest(csr.indptr, csr.indices), csr_data=digest(csr.data), csr_nnz=int(csr.nnz),
+        csc_structure=digest(csc.indptr, csc.indices), csc_data=digest(csc.data), csc_nnz=int(csc.nnz),
+        dense=digest(np.asarray(system.matrix("dense"))),
+    )
+
+
 def main():
     structures = {}
     digests = {}
@@ -85,6 +96,7 @@ def main():
         systems[tag] = system
         for key, val in struct_of(system).items():
             structures[f"{tag}_{key}"] = val
+        digests["formats_" + tag] = format_digests(system)
 
     # ---- digests of the named configs ----------------------------------------------------
     big = {
@@ -150,5 +162,19 @@ def main():
         print(name, os.path.getsize(os.path.join(HERE, name)), "bytes")
 
 
+def formats_only():
+    """Add / refresh only the matrix("csr"/"csc"/"dense") digests in digests.json."""
+    from test_oracle import SMALL
+
+    path = os.path.join(HERE, "digests.json")
+    with open(path) as fh:
+        digests = json.load(fh)
+    for tag, make in SMALL.items():
+        digests["formats_" + tag] = format_digests(make(REF))
+    with open(path, "w") as fh:
+        json.dump(digests, fh, indent=1, sort_keys=True)
+    print("formats:", ", ".join(sorted(SMALL)))
+
+
 if __name__ == "__main__":
-    main()
+    formats_only() if "--formats-only" in sys.argv else main()

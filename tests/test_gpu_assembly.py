@@ -72,6 +72,52 @@ def test_export_formats_and_known_answers(gpu_api):
         system.matrix(format=1)
 
 
+@pytest.mark.parametrize("tag", ["random_3_5_7", "random_2_5_3", "kat_3_5_7", "dwave_9_8_1", "swave3d_5_4_6",
+                                 "junction_30_10_1"])
+def test_scalar_exports_match_reference_and_oracle(gpu_api, digests, tag):
+    """matrix("csr") / ("csc") / ("dense") come from device kernels: bit-exact against
+    the reference's digests and the oracle's restatement (reference hamiltonian.py:144-151)."""
+    from test_oracle import SMALL
+    from util import digest
+
+    system = SMALL[tag](gpu_api)
+    sk = system._matrix
+    want = digests["formats_" + tag]
+    for fmt, transpose in (("csr", False), ("csc", True)):
+        M = system.matrix(fmt)
+        assert M.getformat() == fmt and M.shape == system.shape
+        assert M.indptr.dtype == np.int32 and M.indices.dtype == np.int32 and M.data.dtype == np.complex128
+        optr, oidx, oval = orc.export_scalar(sk.indptr, sk.indices, sk.data, transpose=transpose)
+        assert same_bits(M.indptr, optr) and same_bits(M.indices, oidx) and same_bits(M.data, oval)
+        assert M.nnz == want[f"{fmt}_nnz"]
+        assert digest(M.indptr, M.indices) == want[f"{fmt}_structure"] and digest(M.data) == want[f"{fmt}_data"]
+    dense = np.asarray(system.matrix("dense"))
+    assert digest(dense) == want["dense"]
+    assert same_bits(dense, orc.export_dense(sk.indptr, sk.indices, sk.data))
+
+
+def test_scalar_exports_zero_semantics(gpu_api):
+    """Explicit zeros are dropped element-wise: -0.0 is zero, NaN and denormals are not (scipy's
+    eliminate_zeros on the converted matrix); an empty Hamiltonian exports empty arrays."""
+    system = gpu_api.Hamiltonian(gpu_api.CubicLattice((3, 2, 1)))
+    for fmt in ("csr", "csc"):
+        M = system.matrix(fmt)
+        assert M.nnz == 0 and M.indptr.tolist() == [0] * 25
+    data = system._data
+    data[0, 0, 1] = -0.0
+    data[1, 2, 3] = np.nan
+    data[4, 1, 1] = 5e-324
+    data[7, 3, 0] = 2.5 - 1j
+    system._data = data
+    ref = system._matrix
+    for fmt, conv in (("csr", ref.tocsr), ("csc", ref.tocsc)):
+        R = conv()
+        R.eliminate_zeros()
+        M = system.matrix(fmt)
+        assert same_bits(M.indptr, R.indptr) and same_bits(M.indices, R.indices) and M.nnz == 3
+        assert same_bits(M.data, R.data)
+
+
 def test_hermitian_check_and_errors(gpu_api):
     # reference tests/test_hamiltonian.py:17-57
     system = cases.random_periodic(gpu_api, (3, 5, 7), seed=3)

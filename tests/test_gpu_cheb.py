@@ -446,3 +446,32 @@ def test_dictionary_follows_matrix_updates(gpu_api):
     want = orc.cheb_moments(scipy_of(system), orc.rademacher(2, system.shape[0], np.arange(4)), 32, scale)
     assert not np.array_equal(before, after)
     assert rel_err(after, want) <= TOL
+
+
+# ---- spectral bound from the recursion itself ---------------------------------------
+@pytest.mark.parametrize("tag", ["dwave_9_8_1", "readme_12_12_1", "random_3_5_7", "junction_30_10_1", "swave3d_5_4_6"])
+def test_lanczos_spectral_bound_is_safe_and_tighter(gpu_api, tag):
+    from test_oracle import SMALL
+
+    system = SMALL[tag](gpu_api)
+    lam = float(np.max(np.abs(np.linalg.eigvalsh(np.asarray(system.matrix("dense"))))))
+    loose = system.spectral_bound()
+    tight = system.spectral_bound("lanczos")
+    assert lam < tight <= loose
+    assert tight <= 1.06 * lam
+    # the tighter scale is usable: same free energy as with the row-sum bound, fewer moments needed
+    F_loose = system.free_energy(0.1, cuda=True)
+    F_tight = system.free_energy(0.1, cuda=True, scale=tight)
+    assert abs(F_tight - F_loose) <= 1e-10 * abs(F_loose)
+    with pytest.raises(ValueError):
+        system.spectral_bound("power")
+
+
+def test_boundedness_check_rejects_a_scale_that_is_too_small(gpu_api):
+    """The acceptance test inside spectral_bound("lanczos"): at a scale below max|ε| the recursion blows up."""
+    system = cases.readme_swave(gpu_api, (12, 12, 1))
+    lam = float(np.max(np.abs(np.linalg.eigvalsh(np.asarray(system.matrix("dense"))))))
+    ok = system.chebyshev_moments(258, vectors=4, seed=1, scale=1.001 * lam)[0::2]
+    bad = system.chebyshev_moments(258, vectors=4, seed=1, scale=0.99 * lam)[0::2]
+    assert np.all(ok <= ok[0] * (1 + 1e-9))
+    assert not np.all(bad <= bad[0] * (1 + 1e-9))

@@ -146,3 +146,36 @@ def test_vectorised_resolvent_path_equals_per_energy_path():
     g = np.stack([[(pref[e] / scale) * np.polyval(m[::-1, a], w[e]) for e in range(len(eps))] for a in range(4)])
     got = kpm.ldos_from_resolvent(g.imag[None], eps, energies)[0]
     assert np.allclose(got, want, rtol=1e-11, atol=1e-13)
+
+
+def test_lanczos_coefficients_from_chebyshev_moments():
+    """kpm.jacobi_from_moments: the Jacobi matrix recovered from Chebyshev moments is
+    the one explicit Lanczos steps produce, and its safeguarded top Ritz value bounds the spectrum."""
+    import numpy as np
+
+    from bodge_b200 import kpm
+    from oracle import bdg_oracle as orc
+
+    rng = np.random.default_rng(3)
+    n = 120
+    A = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    A = (A + A.conj().T) / 2
+    lam = np.max(np.abs(np.linalg.eigvalsh(A)))
+    scale = 1.2 * lam
+    x0 = orc.rademacher(5, n, np.arange(1)).astype(np.complex128)
+    import scipy.sparse as sp
+    mu = orc.cheb_moments(sp.csr_matrix(A), x0, 32, scale)[:, 0]
+    alpha, beta = kpm.jacobi_from_moments(mu)
+    v, v_prev, b = x0[:, 0] / np.linalg.norm(x0[:, 0]), np.zeros(n, dtype=complex), 0.0
+    for k in range(12):
+        w = (A / scale) @ v - b * v_prev
+        a_k = np.vdot(v, w).real
+        w = w - a_k * v
+        assert abs(a_k - alpha[k]) <= 1e-8
+        b = np.linalg.norm(w)
+        assert abs(b * b - beta[k]) <= 1e-8
+        v_prev, v = v, w / b
+    ritz, bound = kpm.spectral_radius_from_moments(mu, scale)
+    assert ritz <= lam * (1 + 1e-6) and lam <= bound <= 1.15 * lam
+    with pytest.raises(ValueError):
+        kpm.jacobi_from_moments([0.0, 0.0])

@@ -185,3 +185,19 @@ def test_rademacher_is_counter_based():
     assert set(np.unique(a.real)) == {-1.0, 1.0} and not a.imag.any()
     assert abs(a.real.mean()) < 0.2
     assert not np.array_equal(a, orc.rademacher(8, 64, np.arange(8)))
+
+
+@pytest.mark.parametrize("tag", sorted(SMALL))
+def test_export_formats_match_reference(digests, tag):
+    """matrix("csr") / ("csc") / ("dense") of the reference (hamiltonian.py:144-151), as sha256 of
+    structure and values, against the scipy-free restatement in the oracle."""
+    shape, blocks = record(SMALL[tag])
+    (sp_, si, sd), _ = oracle_assemble(shape, blocks)
+    want = digests["formats_" + tag]
+    for fmt, transpose in (("csr", False), ("csc", True)):
+        ptr, idx, val = orc.export_scalar(sp_, si, sd, transpose=transpose)
+        assert ptr.dtype == np.int32 and idx.dtype == np.int32
+        assert len(idx) == want[f"{fmt}_nnz"]
+        assert digest(ptr, idx) == want[f"{fmt}_structure"]
+        assert digest(val) == want[f"{fmt}_data"]
+    assert digest(orc.export_dense(sp_, si, sd)) == want["dense"]
