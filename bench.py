@@ -172,6 +172,33 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def dict_api_assembly(b, device):
+    """BASELINE config C2 through the reference's own surface -- ``with system as (H, Δ)`` and two
+    Python loops (README.md:73-86) -- to ``matrix("bsr")``.  The user's loops are interpreter time
+    no library can remove; ``library_s`` is everything else (skeleton, dict packing,
+    H2D, scatter + symmetry fill + Hermitian check, zero-block compaction, D2H of the BSR arrays)."""
+    shape = (100, 100, 1)
+    t0 = time.perf_counter()
+    lattice = b.CubicLattice(shape)
+    system = b.Hamiltonian(lattice, device=device)
+    t1 = time.perf_counter()
+    with system as (H, D):
+        for i in lattice.sites():
+            H[i, i] = 3.0 * b.σ0 - 0.05 * b.σ3
+            D[i, i] = -0.10 * b.jσ2
+        for i, j in lattice.bonds():
+            H[i, j] = -1.0 * b.σ0
+        t2 = time.perf_counter()
+    t3 = time.perf_counter()
+    bsr = system.matrix("bsr")
+    t4 = time.perf_counter()
+    return {"config": "C2 CubicLattice((100,100,1)) README s-wave via the dict API", "n_sites": lattice.size,
+            "n_blocks": int(len(bsr.indices)), "sites_per_s": lattice.size / (t4 - t0),
+            "library_sites_per_s": lattice.size / ((t1 - t0) + (t3 - t2) + (t4 - t3)),
+            "user_loop_s": t2 - t1, "skeleton_s": t1 - t0, "exit_s": t3 - t2, "export_bsr_s": t4 - t3,
+            "reference": "6.7-7.1 k sites/s end to end measured for the reference in the build container (SURVEY 6.2)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -215,6 +242,9 @@ def run_ours(args):
         "skeleton_s": t1 - t0, "scatter_check_compact_s": t2 - t1, "h2d_bytes": h2d_bytes, "hermitian_dev": max_dev,
         "what": "bdg_create_cubic + bdg_scatter (pinned host arrays -> device, symmetry fill, Hermitian check) + zero-block compaction",
     }
+
+    if rank == 0:
+        assembly["dict_api"] = dict_api_assembly(b, local)
 
     scale = system.spectral_bound()
     s = system._sys
@@ -260,7 +290,7 @@ def run_ours(args):
     # The same steps on the uncompressed fixed-width matrix copy (every block read from HBM): shows
     # what the block dictionary buys and how close the plain kernel runs to the HBM roofline.
     plain = None
-    if fmt["kernel"] == "dict" and not args.no_plain:
+    if fmt["kernel"].startswith("dict") and not args.no_plain:
         p_total, p_kernel, _, _, p_fmt = timed_steps("ell")
         plain = {"kernel": "cheb_step_ell (every block from HBM)", "kernel_ms_per_launch": p_kernel / K,
                  "steps_per_s": world * K / (p_total * 1e-3), "matrix_bytes_per_launch": p_fmt["matrix_bytes_per_step"]}
@@ -311,7 +341,9 @@ def run_ours(args):
     achieved = bytes_step * K / (kernel_ms * 1e-3) / 1e9
     moved_step = fmt["matrix_bytes_per_step"] + 192 * n_sites * cols
     moved = moved_step * K / (kernel_ms * 1e-3) / 1e9
-    kernel_name = {"dict": "cheb_step_ell<DICT> (block-dictionary matrix)", "ell": "cheb_step_ell",
+    kernel_name = {"dict": "cheb_step_ell<DICT> (block-dictionary matrix)",
+                   "dict_diag": "cheb_step_ell<DICT,DIAG> (block-dictionary matrix, real-diagonal hopping blocks by DFMA)",
+                   "ell": "cheb_step_ell",
                    "dmma": "cheb_step_dmma", "fma": "cheb_step_fma"}.get(fmt["kernel"], fmt["kernel"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(f"{args.config}_k{cols}_{fmt['kernel']}"), "peak_source": peak_src,

@@ -72,6 +72,7 @@ struct RowWalk {
     int Pz = 1, Py = 1;          // patch extents; Pz * Py = warps per CTA
     int nPz = 1, n_patches = 1;  // patches along z, patches in the plane
     int seg_len = 1, n_items = 1;
+    int prefetch = 0;            // rows ahead (a multiple of Ly*Lz) whose records are prefetched into L1; 0 = off
 };
 
 // ---- Chebyshev state ----------------------------------------------------------------------
@@ -116,8 +117,10 @@ struct EllDev {
     // matrix, and one code per slot.  Usable when the distinct blocks are a small fraction of all.
     //   code  int32  [n_sites][width]          table double [n_unique][4][2][4]
     bool dict_usable = false;
+    bool diag_usable = false;  // every block outside slot 0 is real and diagonal: dtab[n_unique][4] holds the diagonals
     int64_t n_unique = 0;
-    DevBuf code, table;
+    DevBuf code, table, dtab;
+    DevBuf tmp_keys, tmp_rep, tmp_where, tmp_dense;  // hash-table scratch of the dictionary build (kept for rebuilds)
 };
 
 struct bdg_system {

@@ -380,7 +380,7 @@ int launch_step(bdg_system *sys, bool first) {
     double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
     const double2 *x_cur = st.vec[st.cur].as<double2>();
     double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
-    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT) {
+    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG) {
         BDG_TRY(ell_launch_step(sys, first, x_cur, x_io, dots_step));
         st.cur ^= 1;
         st.launches += 1;
@@ -451,16 +451,27 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DICT, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DICT_DIAG, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
-    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT) {
+    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT || kernel == BDG_KERNEL_DICT_DIAG) {
         BDG_TRY(ell_build(sys));
         BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
                     "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");
         BDG_REQUIRE(kernel != BDG_KERNEL_DICT || sys->ell.dict_usable,
                     "the block-dictionary kernel needs a fixed-width matrix whose distinct blocks are few");
-        if (kernel == BDG_KERNEL_AUTO)
-            kernel = sys->ell.dict_usable ? BDG_KERNEL_DICT : sys->ell.usable ? BDG_KERNEL_ELL : BDG_KERNEL_DMMA;
+        BDG_REQUIRE(kernel != BDG_KERNEL_DICT_DIAG || sys->ell.diag_usable,
+                    "the diagonal-hopping kernel needs a block dictionary whose off-site blocks are real and diagonal");
+        if (kernel == BDG_KERNEL_AUTO) {
+            // The plain dictionary kernel pays for its bookkeeping only while the matrix is a sizeable
+            // part of the step's traffic (few columns); with many columns the blocks are amortised
+            // anyway and ELL is faster (measured: C3, k = 512).  DICT_DIAG wins at every k measured.
+            const EllDev &e = sys->ell;
+            const bool matrix_matters = 4 * 260 * e.n_sites * e.width >= (int64_t)192 * e.n_sites * n_cols;
+            kernel = e.diag_usable                        ? BDG_KERNEL_DICT_DIAG
+                     : (e.dict_usable && matrix_matters)  ? BDG_KERNEL_DICT
+                     : e.usable                           ? BDG_KERNEL_ELL
+                                                          : BDG_KERNEL_DMMA;
+        }
     }
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;
@@ -482,7 +493,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
 
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
     // walks one contiguous range of block rows (neighbouring rows share their X records in L1).
-    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT) {
+    if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG) {
         BDG_TRY(ell_configure(sys));
     } else {
         int per_sm = 1;
@@ -642,7 +653,7 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     if (kernel) *kernel = st.kernel;
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
-        if (st.kernel == BDG_KERNEL_DICT)
+        if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_ELL)
             *matrix_bytes_per_step = e.n_sites * e.width * 260;

@@ -45,6 +45,12 @@ __device__ __forceinline__ double ld_block(const double *p, uint64_t policy) {
 }
 
 // Table blocks (DICT): a few KB..MB re-read by every row that changes its block pattern -- keep in L1/L2.
+// L1 prefetch of one 128-byte line (SASS: CCTL.E.PF1) -- no register, no scoreboard slot.
+// Predicated for the same reason as ld_table_if below.
+__device__ __forceinline__ void prefetch_l1_if(const void *p, unsigned take) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p prefetch.global.L1 [%0];\n}\n" ::"l"(p), "r"(take));
+}
+
 // Predicated (not branched) so that the row body stays ONE basic block: ptxas schedules per block,
 // and a block boundary between the loads and the MMAs lets it issue an MMA -- and stall on its
 // operands -- before the last loads of the row have been issued.
@@ -59,10 +65,17 @@ __device__ __forceinline__ void ld_table_if(double &v, const double *p, unsigned
 // from one row of the warp to the next and a slot is re-fetched only when its code changes
 // (warp-uniform test), so on a lattice with a few distinct hopping / on-site terms the matrix
 // costs 8 bytes per block of HBM traffic instead of 260 and no L1 wavefronts at all.
-template <int PW, int CH, int NP, int PB, bool DICT>
+//
+// DIAG (with DICT) = every block outside slot 0 is REAL and DIAGONAL (spin-independent or sigma_3
+// hopping without pairing on the bonds: -t sigma_0 becomes diag(-t, -t, t, t)).  Such a block scales
+// the lane's own element of the neighbour record, so it costs two DFMA instead of two DMMA (which
+// occupy the FP64 pipe 16 cycles each) and the held "fragment" is the lane's diagonal entry from
+// `dtab[code][4]`.  Once the dictionary has taken the matrix out of the HBM stream the FP64 pipe is
+// the next limiter (ncu: math-pipe-throttle stalls), which this removes for the common models.
+template <int PW, int CH, int NP, int PB, bool DICT, bool DIAG>
 __global__ void __launch_bounds__(kThreads, 4)
 cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode, const double *__restrict__ cdata,
-              const double2 *__restrict__ x_cur, double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha,
+              const double *__restrict__ dtab, const double2 *__restrict__ x_cur, double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha,
               double beta, int first, int stream_matrix, double *__restrict__ partials,
               unsigned *__restrict__ tickets, double *__restrict__ dots_step, const RowWalk wk) {
     constexpr int REC = PW * 4;           // complex elements per site record
@@ -106,6 +119,17 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
     int jv = 0;
     if (row >= 0 && ilane) jv = __ldg(islot + (size_t)row * CH + lane);
 
+    // March prefetch: the only records of a step that are not in L1 yet are the +x neighbour's T_n
+    // and the row's own T_{n-1}; both addresses are known `wk.prefetch` rows ahead.  Lanes 0..LINES-1
+    // fetch the lines of T_n[row + prefetch + M], the next LINES lanes those of T_{n-1}[row + prefetch].
+    constexpr int LINES = (REC * 16 + 127) / 128;
+    const bool pf_prev = lane >= LINES;
+    const char *pf_base = pf_prev ? reinterpret_cast<const char *>(x_io) + (size_t)(lane - LINES) * 128
+                                  : reinterpret_cast<const char *>(x_cur + (size_t)M * REC) + (size_t)lane * 128;
+    const int pf_limit = n_sites - (pf_prev ? 0 : M);           // first row past the prefetchable range
+    // (only the dictionary kernel: the plain one is HBM-bound and gains nothing from shorter stalls)
+    const bool pf_lane = DICT && NP == 1 && wk.prefetch > 0 && lane < (first ? LINES : 2 * LINES);
+
     double d0[NP], d1[NP];
 #pragma unroll
     for (int pp = 0; pp < NP; ++pp) d0[pp] = d1[pp] = 0.0;
@@ -125,7 +149,8 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
 #pragma unroll
             for (int u = 0; u < CH; ++u) {
                 const int code = __shfl_sync(kFull, jv, 8 + u);
-                ld_table_if(keep[u], cdata + (size_t)code * 32 + lane, changed >> u & 1u);
+                const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : cdata + (size_t)code * 32 + lane;
+                ld_table_if(keep[u], entry, changed >> u & 1u);
                 bop[u] = keep[u];
             }
         } else {
@@ -135,6 +160,11 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
         }
         int jnext = 0;
         if (nrow >= 0 && ilane) jnext = __ldg(islot + (size_t)nrow * CH + lane);
+        if (DICT && NP == 1) {
+            const int prow = row + wk.prefetch;
+            prefetch_l1_if(pf_base + ((size_t)panel0 * plane + (size_t)prow * REC) * sizeof(double2),
+                           pf_lane && prow < pf_limit);
+        }
         const size_t off = (size_t)row * REC + x_elem;
 
 #pragma unroll
@@ -155,11 +185,18 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
             for (int pp = 0; pp < PB; ++pp) {
                 double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
+                for (int u = 0; u < (DIAG ? 1 : CH); ++u) {
                     dmma_8x8x4(a10, a11, xv[pp][u].x, bop[u]);
                     dmma_8x8x4(a20, a21, xv[pp][u].y, bop[u]);
                 }
-                const double yr = a10 - a21, yi = a11 + a20;
+                double yr = a10 - a21, yi = a11 + a20;
+                if (DIAG) {
+#pragma unroll
+                    for (int u = 1; u < CH; ++u) {
+                        yr = fma(bop[u], xv[pp][u].x, yr);
+                        yi = fma(bop[u], xv[pp][u].y, yi);
+                    }
+                }
                 if (on[pp] && x_lane) {
                     const double2 tn = xv[pp][0];  // slot 0 is the row's own record
                     const double2 out = make_double2(alpha * yr - beta * pv[pp].x, alpha * yi - beta * pv[pp].y);
@@ -240,10 +277,13 @@ ell_fill(int n_sites, int width, const int32_t *__restrict__ indptr, const int32
 constexpr unsigned long long kEmptyKey = ~0ull;
 
 // One warp per slot: hash, find-or-insert, remember the table position and the smallest slot id
-// holding that key (the representative whose bytes become the table entry).
+// holding that key (the representative whose bytes become the table entry).  The table is sized
+// for few distinct blocks; when more than `limit` keys have been inserted the pass is abandoned
+// (*overflow = 1) and the host retries with a larger table or gives the format up.
 __global__ void __launch_bounds__(256)
 dict_insert(int64_t n_slots, const double *__restrict__ cdata, unsigned long long *__restrict__ keys,
-            int *__restrict__ rep, unsigned cap_mask, int32_t *__restrict__ where) {
+            int *__restrict__ rep, unsigned cap_mask, int32_t *__restrict__ where, int *__restrict__ counter,
+            int limit, int *__restrict__ overflow) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_slots) return;
@@ -257,8 +297,15 @@ dict_insert(int64_t n_slots, const double *__restrict__ cdata, unsigned long lon
     unsigned pos = (unsigned)h & cap_mask;
     for (;;) {
         unsigned long long seen = *((volatile unsigned long long *)(keys + pos));  // cheap hit for repeated blocks
-        if (seen == kEmptyKey) seen = atomicCAS(keys + pos, kEmptyKey, (unsigned long long)h);
+        if (seen == kEmptyKey) {
+            seen = atomicCAS(keys + pos, kEmptyKey, (unsigned long long)h);
+            if (seen == kEmptyKey && atomicAdd(counter, 1) >= limit) *overflow = 1;
+        }
         if (seen == kEmptyKey || seen == h) break;
+        if (*((volatile int *)overflow)) {
+            where[w] = 0;
+            return;
+        }
         pos = (pos + 1) & cap_mask;
     }
     if (*((volatile int *)(rep + pos)) > (int)w) atomicMin(rep + pos, (int)w);
@@ -292,35 +339,61 @@ dict_emit(int64_t n_slots, const double *__restrict__ cdata, const int *__restri
     if (lane == 0) ccode[w] = code;
 }
 
-using EllKernel = void (*)(const int32_t *, const int32_t *, const double *, const double2 *, double2 *, int, int,
-                           double, double, int, int, double *, unsigned *, double *, const RowWalk);
+// dtab[code][a] = Re of diagonal entry (a, a) of table block `code`; isdiag[code] = the block has
+// nothing else (all other real and imaginary parts compare == 0).
+__global__ void __launch_bounds__(256)
+dict_diag_table(int n_unique, const double *__restrict__ table, double *__restrict__ dtab, int *__restrict__ isdiag) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_unique) return;
+    const double v = table[(size_t)w * 32 + lane];
+    const int a = lane >> 3, part = (lane >> 2) & 1, b = lane & 3;  // double `lane` = part (re/im) of entry (a, b)
+    const bool on_diag = part == 0 && a == b;
+    const unsigned other = __ballot_sync(0xffffffffu, !on_diag && v != 0.0);
+    if (on_diag) dtab[(size_t)w * 4 + a] = v;
+    if (lane == 0) isdiag[w] = other == 0u;
+}
 
-template <int PW, int NP, int PB, bool DICT> EllKernel pick_ch(int width) {
+// *bad = 1 if any slot other than slot 0 holds a block that is not real-diagonal.
+__global__ void __launch_bounds__(256)
+dict_offsite_diag(int64_t n_slots, int width, const int32_t *__restrict__ ccode, const int *__restrict__ isdiag,
+                  int *__restrict__ bad) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slots || t % width == 0) return;
+    if (!isdiag[ccode[t]]) *bad = 1;
+}
+
+using EllKernel = void (*)(const int32_t *, const int32_t *, const double *, const double *, const double2 *, double2 *,
+                           int, int, double, double, int, int, double *, unsigned *, double *, const RowWalk);
+
+template <int PW, int NP, int PB, bool DICT, bool DIAG> EllKernel pick_ch(int width) {
     switch (width) {
-        case 3: return cheb_step_ell<PW, 3, NP, PB, DICT>;
-        case 4: return cheb_step_ell<PW, 4, NP, PB, DICT>;
-        case 5: return cheb_step_ell<PW, 5, NP, PB, DICT>;
-        case 6: return cheb_step_ell<PW, 6, NP, PB, DICT>;
-        case 7: return cheb_step_ell<PW, 7, NP, PB, DICT>;
-        default: return cheb_step_ell<PW, 8, NP, PB, DICT>;
+        case 3: return cheb_step_ell<PW, 3, NP, PB, DICT, DIAG>;
+        case 4: return cheb_step_ell<PW, 4, NP, PB, DICT, DIAG>;
+        case 5: return cheb_step_ell<PW, 5, NP, PB, DICT, DIAG>;
+        case 6: return cheb_step_ell<PW, 6, NP, PB, DICT, DIAG>;
+        case 7: return cheb_step_ell<PW, 7, NP, PB, DICT, DIAG>;
+        default: return cheb_step_ell<PW, 8, NP, PB, DICT, DIAG>;
     }
 }
 
-template <bool DICT> EllKernel pick_shape(int pw, int np, int pb, int width) {
+template <bool DICT, bool DIAG> EllKernel pick_shape(int pw, int np, int pb, int width) {
     switch (pw) {
-        case 1: return pick_ch<1, 1, 1, DICT>(width);
-        case 2: return pick_ch<2, 1, 1, DICT>(width);
-        case 4: return pick_ch<4, 1, 1, DICT>(width);
+        case 1: return pick_ch<1, 1, 1, DICT, DIAG>(width);
+        case 2: return pick_ch<2, 1, 1, DICT, DIAG>(width);
+        case 4: return pick_ch<4, 1, 1, DICT, DIAG>(width);
         default:
-            if (np >= 8) return pick_ch<8, 8, 1, DICT>(width);
-            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2, DICT>(width) : pick_ch<8, 4, 1, DICT>(width);
-            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2, DICT>(width) : pick_ch<8, 2, 1, DICT>(width);
-            return pick_ch<8, 1, 1, DICT>(width);
+            if (np >= 8) return pick_ch<8, 8, 1, DICT, DIAG>(width);
+            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2, DICT, DIAG>(width) : pick_ch<8, 4, 1, DICT, DIAG>(width);
+            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2, DICT, DIAG>(width) : pick_ch<8, 2, 1, DICT, DIAG>(width);
+            return pick_ch<8, 1, 1, DICT, DIAG>(width);
     }
 }
 
-EllKernel pick_ell(bool dict, int pw, int np, int pb, int width) {
-    return dict ? pick_shape<true>(pw, np, pb, width) : pick_shape<false>(pw, np, pb, width);
+// fmt: BDG_KERNEL_ELL, BDG_KERNEL_DICT or BDG_KERNEL_DICT_DIAG
+EllKernel pick_ell(int fmt, int pw, int np, int pb, int width) {
+    if (fmt == BDG_KERNEL_DICT_DIAG) return pick_shape<true, true>(pw, np, pb, width);
+    if (fmt == BDG_KERNEL_DICT) return pick_shape<true, false>(pw, np, pb, width);
+    return pick_shape<false, false>(pw, np, pb, width);
 }
 
 int env_int(const char *name, int fallback) {
@@ -364,6 +437,7 @@ RowWalk plan_walk(const bdg_system *sys, int n_sites, int64_t slots) {
         }
         if (forced > 0) break;
     }
+    w.prefetch = std::max(0, env_int("BDG_ELL_PREFETCH", 2)) * Ly * Lz;
     return w;
 }
 
@@ -374,76 +448,65 @@ int dict_build(bdg_system *sys) {
     e.n_unique = 0;
     const int64_t n_slots = e.n_sites * e.width;
     if (n_slots <= 0 || n_slots > (int64_t)1 << 30) return BDG_OK;
-    int64_t cap = 1024;
-    while (cap < 2 * n_slots) cap <<= 1;
-    DevBuf keys, rep, where, dense;
-    int rc = BDG_OK;
-    auto cleanup = [&]() {
-        dev_free(sys, keys);
-        dev_free(sys, rep);
-        dev_free(sys, where);
-        dev_free(sys, dense);
-    };
-#define DICT_TRY(expr)            \
-    do {                          \
-        rc = (expr);              \
-        if (rc != BDG_OK) {       \
-            cleanup();            \
-            return rc;            \
-        }                         \
-    } while (0)
-#define DICT_CUDA(expr)                                                                          \
-    do {                                                                                         \
-        cudaError_t err__ = (expr);                                                              \
-        if (err__ != cudaSuccess) {                                                              \
-            bdg_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                  \
-                          cudaGetErrorString(err__));                                            \
-            cleanup();                                                                           \
-            return BDG_E_CUDA;                                                                   \
-        }                                                                                        \
-    } while (0)
-    DICT_TRY(dev_alloc(sys, keys, (size_t)cap * sizeof(unsigned long long)));
-    DICT_TRY(dev_alloc(sys, rep, (size_t)cap * sizeof(int)));
-    DICT_TRY(dev_alloc(sys, where, (size_t)n_slots * sizeof(int32_t)));
-    DICT_TRY(dev_alloc(sys, dense, (size_t)(cap + 1) * sizeof(int32_t)));
-    DICT_TRY(ensure_scratch(sys, 2, 64));
-    int *scal = sys->scratch_i32[2].as<int>();  // [0] = number of distinct blocks, [1] = mismatch flag
-    DICT_CUDA(cudaMemsetAsync(keys.ptr, 0xff, (size_t)cap * sizeof(unsigned long long), sys->stream));
-    DICT_CUDA(cudaMemsetAsync(rep.ptr, 0x7f, (size_t)cap * sizeof(int), sys->stream));
-    DICT_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(int), sys->stream));
-    const unsigned warps_grid = (unsigned)ceil_div(n_slots * 32, 256);
-    dict_insert<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), keys.as<unsigned long long>(),
-                                                     rep.as<int>(), (unsigned)(cap - 1), where.as<int32_t>());
-    dict_flag_used<<<(unsigned)ceil_div(cap, 256), 256, 0, sys->stream>>>(cap, keys.as<unsigned long long>(),
-                                                                          dense.as<int32_t>());
-    DICT_CUDA(cudaGetLastError());
-    DICT_TRY(exclusive_scan_i32(sys, dense.as<int32_t>(), dense.as<int32_t>(), cap, scal));
-    int n_unique = 0;
-    DICT_CUDA(cudaMemcpyAsync(&n_unique, scal, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
-    DICT_CUDA(cudaStreamSynchronize(sys->stream));
-    e.n_unique = n_unique;
     // Worth it when the table is a small fraction of the matrix (each distinct block is still
     // read from HBM about once per step; the codes cost 4 bytes per slot).
-    const int max_frac = env_int("BDG_DICT_MAX_PERCENT", 35);
-    if ((int64_t)n_unique * 100 <= n_slots * max_frac) {
-        DICT_TRY(dev_alloc(sys, e.code, (size_t)n_slots * sizeof(int32_t)));
-        DICT_TRY(dev_alloc(sys, e.table, (size_t)n_unique * 32 * sizeof(double)));
-        dict_emit<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), rep.as<int>(), dense.as<int32_t>(),
-                                                       where.as<int32_t>(), e.code.as<int32_t>(), e.table.as<double>(),
-                                                       n_unique, scal + 1);
-        DICT_CUDA(cudaGetLastError());
-        int mismatch = 0;
-        DICT_CUDA(cudaMemcpyAsync(&mismatch, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
-        DICT_CUDA(cudaStreamSynchronize(sys->stream));
-        e.dict_usable = mismatch == 0;
+    const int64_t max_unique = std::max<int64_t>(1, n_slots * env_int("BDG_DICT_MAX_PERCENT", 35) / 100);
+    BDG_TRY(dev_alloc(sys, e.tmp_where, (size_t)n_slots * sizeof(int32_t)));
+    BDG_TRY(ensure_scratch(sys, 2, 64));
+    int *scal = sys->scratch_i32[2].as<int>();  // [0] keys inserted, [1] overflow, [2] distinct (scan), [3] mismatch
+    const unsigned warps_grid = (unsigned)ceil_div(n_slots * 32, 256);
+    // Lattice Hamiltonians have a handful of distinct blocks: start with a small table (cheap to
+    // clear and to scan) and grow it only when it fills up.
+    int64_t cap = 1 << 16;
+    int host[4] = {0, 0, 0, 0};
+    for (;;) {
+        const int limit = (int)std::min<int64_t>(cap / 2, max_unique);
+        BDG_TRY(dev_alloc(sys, e.tmp_keys, (size_t)cap * sizeof(unsigned long long)));
+        BDG_TRY(dev_alloc(sys, e.tmp_rep, (size_t)cap * sizeof(int)));
+        BDG_TRY(dev_alloc(sys, e.tmp_dense, (size_t)(cap + 1) * sizeof(int32_t)));
+        BDG_CUDA(cudaMemsetAsync(e.tmp_keys.ptr, 0xff, (size_t)cap * sizeof(unsigned long long), sys->stream));
+        BDG_CUDA(cudaMemsetAsync(e.tmp_rep.ptr, 0x7f, (size_t)cap * sizeof(int), sys->stream));
+        BDG_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), sys->stream));
+        dict_insert<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), e.tmp_keys.as<unsigned long long>(),
+                                                         e.tmp_rep.as<int>(), (unsigned)(cap - 1), e.tmp_where.as<int32_t>(),
+                                                         scal, limit, scal + 1);
+        BDG_CUDA(cudaGetLastError());
+        BDG_CUDA(cudaMemcpyAsync(host, scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+        e.n_unique = host[0];  // exact unless the pass was abandoned (then: at least this many)
+        if (!host[1]) break;
+        if (limit >= max_unique) return BDG_OK;  // too many distinct blocks: keep the plain format
+        cap <<= 4;
     }
-    if (!e.dict_usable) {
-        dev_free(sys, e.code);
-        dev_free(sys, e.table);
+    dict_flag_used<<<(unsigned)ceil_div(cap, 256), 256, 0, sys->stream>>>(cap, e.tmp_keys.as<unsigned long long>(),
+                                                                          e.tmp_dense.as<int32_t>());
+    BDG_CUDA(cudaGetLastError());
+    BDG_TRY(exclusive_scan_i32(sys, e.tmp_dense.as<int32_t>(), e.tmp_dense.as<int32_t>(), cap, scal + 2));
+    const int n_unique = host[0];
+    BDG_TRY(dev_alloc(sys, e.code, (size_t)n_slots * sizeof(int32_t)));
+    BDG_TRY(dev_alloc(sys, e.table, (size_t)n_unique * 32 * sizeof(double)));
+    dict_emit<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), e.tmp_rep.as<int>(),
+                                                   e.tmp_dense.as<int32_t>(), e.tmp_where.as<int32_t>(),
+                                                   e.code.as<int32_t>(), e.table.as<double>(), n_unique, scal + 3);
+    BDG_CUDA(cudaGetLastError());
+    BDG_CUDA(cudaMemcpyAsync(host + 2, scal + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+    BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    e.dict_usable = host[3] == 0 && host[2] == n_unique;  // no hash collision, table fully written
+    // Real-diagonal off-site blocks (DIAG kernels)?
+    e.diag_usable = false;
+    if (e.dict_usable) {
+        BDG_TRY(dev_alloc(sys, e.dtab, (size_t)n_unique * 4 * sizeof(double)));
+        BDG_TRY(dev_alloc(sys, e.tmp_rep, (size_t)std::max<int64_t>(cap, n_unique) * sizeof(int)));  // reuse as isdiag[]
+        BDG_CUDA(cudaMemsetAsync(scal, 0, sizeof(int), sys->stream));
+        dict_diag_table<<<(unsigned)ceil_div((int64_t)n_unique * 32, 256), 256, 0, sys->stream>>>(
+            n_unique, e.table.as<double>(), e.dtab.as<double>(), e.tmp_rep.as<int>());
+        dict_offsite_diag<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(
+            n_slots, e.width, e.code.as<int32_t>(), e.tmp_rep.as<int>(), scal);
+        BDG_CUDA(cudaGetLastError());
+        BDG_CUDA(cudaMemcpyAsync(host, scal, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+        e.diag_usable = host[0] == 0;
     }
-    cleanup();
-#undef DICT_TRY
-#undef DICT_CUDA
     return BDG_OK;
 }
 
@@ -454,6 +517,11 @@ void ell_release(bdg_system *sys) {
     dev_free(sys, sys->ell.data);
     dev_free(sys, sys->ell.code);
     dev_free(sys, sys->ell.table);
+    dev_free(sys, sys->ell.dtab);
+    dev_free(sys, sys->ell.tmp_keys);
+    dev_free(sys, sys->ell.tmp_rep);
+    dev_free(sys, sys->ell.tmp_where);
+    dev_free(sys, sys->ell.tmp_dense);
     sys->ell = EllDev();
 }
 
@@ -465,6 +533,7 @@ int ell_build(bdg_system *sys) {
     const int n = (int)m.n_sites;
     e.usable = false;
     e.dict_usable = false;
+    e.diag_usable = false;
     e.n_unique = 0;
     e.n_sites = n;
     if (n > 0) {
@@ -501,7 +570,6 @@ int ell_build(bdg_system *sys) {
 int ell_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const bool dict = st.kernel == BDG_KERNEL_DICT;
     // Measured (profiles/r01/sweep_ell_v1.log): these kernels are latency-bound once the vectors
     // dominate, so occupancy (24 warps/SM at one panel per warp-row) beats reusing the block
     // registers for 4 or 8 panels (16 warps/SM) -- concurrent panel groups sweep the lattice in
@@ -521,7 +589,7 @@ int ell_configure(bdg_system *sys) {
     st.n_groups = (int)ceil_div(st.n_panels, st.panels_per_group);
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, pick_ell(dict, st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads,
+        &per_sm, pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads,
         (size_t)env_int("BDG_ELL_PAD", 0)));
     per_sm = std::max(per_sm, 1);
     const int64_t slots = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_groups);
@@ -533,8 +601,8 @@ int ell_configure(bdg_system *sys) {
 int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const bool dict = st.kernel == BDG_KERNEL_DICT;
-    EllKernel k = pick_ell(dict, st.panel_width, st.panels_per_group, st.panel_batch, e.width);
+    const bool dict = st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG;
+    EllKernel k = pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width);
     // Stream the matrix through L2 (evict-first) only when nothing will read it again soon: one
     // group per pass and a matrix that cannot stay resident in the 126 MB L2 anyway.
     const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;
@@ -543,7 +611,7 @@ int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, 
     const size_t pad = (size_t)env_int("BDG_ELL_PAD", 0);  // occupancy experiments: unused dynamic shared memory
     if (pad > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
     k<<<grid, kThreads, pad, sys->stream>>>(e.idx.as<int32_t>(), dict ? e.code.as<int32_t>() : nullptr,
-                                          dict ? e.table.as<double>() : e.data.as<double>(),
+                                          dict ? e.table.as<double>() : e.data.as<double>(), e.dtab.as<double>(),
                                           static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_io),
                                           (int)e.n_sites, st.n_panels, (first ? 1.0 : 2.0) / st.scale, first ? 0.0 : 1.0,
                                           first ? 1 : 0, stream_matrix, st.partials.as<double>(),

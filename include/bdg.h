@@ -110,7 +110,10 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
  *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
-/* AUTO = DICT when the matrix qualifies, else ELL when it qualifies, else DMMA.
+/* AUTO = DICT_DIAG, else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+ * DICT_DIAG = DICT for matrices whose blocks off the lattice diagonal are all real and diagonal (hopping
+ *        -t sigma_0 / m sigma_3 without pairing on the bonds): those blocks cost two DFMA instead of two
+ *        FP64 MMAs.  Same sums in a different rounding order than DICT / ELL (agrees to ~1e-15);
  * DICT = the ELL kernel on a block-dictionary copy of the matrix: the distinct 4x4 blocks once, plus a
  *        4-byte code per block.  Lattice Hamiltonians repeat a handful of hopping / on-site blocks
  *        millions of times, so the per-step matrix traffic drops from 260 to 8 bytes per block; the
@@ -122,7 +125,7 @@ enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
  * FMA  = scalar formulation (A/B reference); SIMPLE / CHUNKED = unpipelined DMMA with wavefront /
  *        per-CTA-chunk row traversal (tuning references). */
 enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_ELL = 3,
-       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6 };
+       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6, BDG_KERNEL_DICT_DIAG = 7 };
 
 /* Start a recursion on n_cols start vectors resident on this GPU.
  *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)
