@@ -164,6 +164,8 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
             const int prow = row + wk.prefetch;
             prefetch_l1_if(pf_base + ((size_t)panel0 * plane + (size_t)prow * REC) * sizeof(double2),
                            pf_lane && prow < pf_limit);
+            // ... and the index / code lines of the row after next (jnext covers the next one)
+            prefetch_l1_if(islot + (size_t)(prow + M) * CH + lane, wk.prefetch > 0 && ilane && prow + M < n_sites);
         }
         const size_t off = (size_t)row * REC + x_elem;
 
