@@ -107,7 +107,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, watts, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -115,12 +115,17 @@ class ClockSampler:
                 mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
+            try:
+                watts.append(float(r[2]))
+            except (ValueError, IndexError):
+                pass
             for name, val in zip(names, r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(watts) if watts else None}
 
 
 # ------------------------------------------------------------------------------------------
@@ -227,20 +232,39 @@ def run_ours(args):
     h2d_bytes = sum(a.nbytes for a in host)
 
     # ---- assembly (timed separately: the second half of BASELINE.json's metric) ---------------
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    system = b.Hamiltonian(b.CubicLattice(shape), device=local)
-    system._sys.sync()
-    t1 = time.perf_counter()
-    max_dev = system.fill(*host)
-    info0 = system._sys.cheb_info()  # builds the compacted BSR the Chebyshev engine consumes
-    system._sys.sync()
-    t2 = time.perf_counter()
+    # One untimed warm-up (lazy module loading, first allocations), then the median of three full
+    # assemblies: skeleton on the device, H2D of the packed Hamiltonian terms from pinned host memory,
+    # scatter + symmetry fill + Hermitian check, zero-block compaction.  Everything a Hamiltonian owns
+    # is released in between (bdg_destroy), so every repetition allocates its 1.3 GB again.
+    def assemble_once():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sysm = b.Hamiltonian(b.CubicLattice(shape), device=local)
+        sysm._sys.sync()
+        t1 = time.perf_counter()
+        dev = sysm.fill(*host)
+        sysm._sys.sync()
+        t2 = time.perf_counter()
+        nfo = sysm._sys.cheb_info()  # builds the compacted BSR the Chebyshev engine consumes
+        sysm._sys.sync()
+        t3 = time.perf_counter()
+        return sysm, dev, nfo, (t1 - t0, t2 - t1, t3 - t2)
+
+    system, max_dev, info0, cold = assemble_once()
+    reps = []
+    for _ in range(3):
+        del system
+        system, max_dev, info0, times = assemble_once()
+        reps.append(times)
+    reps.sort(key=sum)
+    t_skel, t_fill, t_pack = reps[1]
     n_sites = system.lattice.size
     assembly = {
-        "sites_per_s": n_sites / (t2 - t0), "unit": "sites/s", "n_sites": n_sites, "n_blocks": info0["n_blocks"],
-        "skeleton_s": t1 - t0, "scatter_check_compact_s": t2 - t1, "h2d_bytes": h2d_bytes, "hermitian_dev": max_dev,
-        "what": "bdg_create_cubic + bdg_scatter (pinned host arrays -> device, symmetry fill, Hermitian check) + zero-block compaction",
+        "sites_per_s": n_sites / (t_skel + t_fill + t_pack), "unit": "sites/s", "n_sites": n_sites,
+        "n_blocks": info0["n_blocks"], "skeleton_s": t_skel, "h2d_scatter_check_s": t_fill, "compaction_s": t_pack,
+        "cold_first_call_s": sum(cold), "h2d_bytes": h2d_bytes, "hermitian_dev": max_dev,
+        "what": "median of 3 after 1 warm-up: bdg_create_cubic + bdg_scatter (pinned host arrays -> device, symmetry "
+                "fill, Hermitian check) + zero-block compaction",
     }
 
     if rank == 0:

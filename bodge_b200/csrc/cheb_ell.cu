@@ -119,16 +119,29 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
     int jv = 0;
     if (row >= 0 && ilane) jv = __ldg(islot + (size_t)row * CH + lane);
 
-    // March prefetch: the only records of a step that are not in L1 yet are the +x neighbour's T_n
-    // and the row's own T_{n-1}; both addresses are known `wk.prefetch` rows ahead.  Lanes 0..LINES-1
-    // fetch the lines of T_n[row + prefetch + M], the next LINES lanes those of T_{n-1}[row + prefetch].
+    // March prefetch: the records of a step that are not in L1 yet are the +x neighbour's T_n, the
+    // row's own T_{n-1} and -- for the warps on the rim of the patch -- the z / y neighbours owned by
+    // other CTAs.  All their addresses are known `wk.prefetch` rows ahead.  Lane groups of LINES lanes
+    // (one lane per 128-byte line of a record): 0 = T_n[+M], 1 = T_{n-1}[0], 2 = T_n[z halo], 3 = T_n[y halo].
     constexpr int LINES = (REC * 16 + 127) / 128;
-    const bool pf_prev = lane >= LINES;
-    const char *pf_base = pf_prev ? reinterpret_cast<const char *>(x_io) + (size_t)(lane - LINES) * 128
-                                  : reinterpret_cast<const char *>(x_cur + (size_t)M * REC) + (size_t)lane * 128;
-    const int pf_limit = n_sites - (pf_prev ? 0 : M);           // first row past the prefetchable range
-    // (only the dictionary kernel: the plain one is HBM-bound and gains nothing from shorter stalls)
-    const bool pf_lane = DICT && NP == 1 && wk.prefetch > 0 && lane < (first ? LINES : 2 * LINES);
+    const int pf_group = lane / LINES;
+    int pf_delta = 0;           // row offset of the record this lane prefetches
+    bool pf_lane = DICT && NP == 1 && wk.prefetch > 0;
+    {
+        const int dz = warp % wk.Pz, dy = warp / wk.Pz;
+        if (pf_group == 0) pf_delta = M;
+        else if (pf_group == 1) pf_lane = pf_lane && !first;
+        else if (pf_group == 2) {
+            pf_delta = dz == 0 ? -1 : 1;
+            pf_lane = pf_lane && wk.Lz > 1 && (dz == 0 || dz == wk.Pz - 1);
+        } else if (pf_group == 3) {
+            pf_delta = dy == 0 ? -wk.Lz : wk.Lz;
+            pf_lane = pf_lane && wk.Ly > 1 && wk.Lx > 1 && (dy == 0 || dy == wk.Py - 1);
+        } else {
+            pf_lane = false;
+        }
+    }
+    const char *pf_base = reinterpret_cast<const char *>(pf_group == 1 ? x_io : x_cur) + (size_t)(lane % LINES) * 128;
 
     double d0[NP], d1[NP];
 #pragma unroll
@@ -144,15 +157,21 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
         for (int u = 0; u < CH; ++u) jn[u] = __shfl_sync(kFull, jv, u);
         double bop[CH];
         if (DICT) {
-            const unsigned changed = __ballot_sync(kFull, jv != jheld) >> 8;  // warp-uniform
-            jheld = jv;
+            // Reload the held fragments only when a code differs from the previous row's (warp-uniform
+            // and rare inside a homogeneous region).  The branch sits BEFORE the row's loads so that
+            // loads and MMAs still share one basic block.
+            const unsigned changed = __ballot_sync(kFull, jv != jheld) >> 8;
+            if (changed) {
+                jheld = jv;
 #pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                const int code = __shfl_sync(kFull, jv, 8 + u);
-                const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : cdata + (size_t)code * 32 + lane;
-                ld_table_if(keep[u], entry, changed >> u & 1u);
-                bop[u] = keep[u];
+                for (int u = 0; u < CH; ++u) {
+                    const int code = __shfl_sync(kFull, jv, 8 + u);
+                    const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : cdata + (size_t)code * 32 + lane;
+                    ld_table_if(keep[u], entry, changed >> u & 1u);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) bop[u] = keep[u];
         } else {
             const double *blk = cdata + (size_t)row * CH * 32 + lane;
 #pragma unroll
@@ -161,11 +180,12 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
         int jnext = 0;
         if (nrow >= 0 && ilane) jnext = __ldg(islot + (size_t)nrow * CH + lane);
         if (DICT && NP == 1) {
-            const int prow = row + wk.prefetch;
+            const int prow = row + wk.prefetch + pf_delta;
             prefetch_l1_if(pf_base + ((size_t)panel0 * plane + (size_t)prow * REC) * sizeof(double2),
-                           pf_lane && prow < pf_limit);
+                           pf_lane && prow >= 0 && prow < n_sites);
             // ... and the index / code lines of the row after next (jnext covers the next one)
-            prefetch_l1_if(islot + (size_t)(prow + M) * CH + lane, wk.prefetch > 0 && ilane && prow + M < n_sites);
+            const int irow = row + wk.prefetch + M;
+            prefetch_l1_if(islot + (size_t)irow * CH + lane, wk.prefetch > 0 && ilane && irow < n_sites);
         }
         const size_t off = (size_t)row * REC + x_elem;
 
@@ -439,7 +459,7 @@ RowWalk plan_walk(const bdg_system *sys, int n_sites, int64_t slots) {
         }
         if (forced > 0) break;
     }
-    w.prefetch = std::max(0, env_int("BDG_ELL_PREFETCH", 2)) * Ly * Lz;
+    w.prefetch = std::max(0, env_int("BDG_ELL_PREFETCH", 1)) * Ly * Lz;
     return w;
 }
 

@@ -28,7 +28,7 @@ for item in sys.argv[1:]:
         s.sync()
         t_begin = time.time() - t0
         s.cheb_steps(10, timed=True)
-        steps = 100
+        steps = int(os.environ.get("QP_STEPS", "100"))  # 100 = burst clocks; >= 2000 = sustained under the power cap
         ms = s.cheb_steps(steps, timed=True)
         info, fmt = s.cheb_info(), s.cheb_format()
         gbs = info["bytes_per_step"] * steps / (ms * 1e-3) / 1e9
