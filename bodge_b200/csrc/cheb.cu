@@ -461,17 +461,11 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
                     "the block-dictionary kernel needs a fixed-width matrix whose distinct blocks are few");
         BDG_REQUIRE(kernel != BDG_KERNEL_DICT_DIAG || sys->ell.diag_usable,
                     "the diagonal-hopping kernel needs a block dictionary whose off-site blocks are real and diagonal");
-        if (kernel == BDG_KERNEL_AUTO) {
-            // The plain dictionary kernel pays for its bookkeeping only while the matrix is a sizeable
-            // part of the step's traffic (few columns); with many columns the blocks are amortised
-            // anyway and ELL is faster (measured: C3, k = 512).  DICT_DIAG wins at every k measured.
-            const EllDev &e = sys->ell;
-            const bool matrix_matters = 4 * 260 * e.n_sites * e.width >= (int64_t)192 * e.n_sites * n_cols;
-            kernel = e.diag_usable                        ? BDG_KERNEL_DICT_DIAG
-                     : (e.dict_usable && matrix_matters)  ? BDG_KERNEL_DICT
-                     : e.usable                           ? BDG_KERNEL_ELL
-                                                          : BDG_KERNEL_DMMA;
-        }
+        if (kernel == BDG_KERNEL_AUTO)
+            kernel = sys->ell.diag_usable   ? BDG_KERNEL_DICT_DIAG
+                     : sys->ell.dict_usable ? BDG_KERNEL_DICT
+                     : sys->ell.usable      ? BDG_KERNEL_ELL
+                                            : BDG_KERNEL_DMMA;
     }
     const BsrDev &m = sys->packed;
     const int n = (int)m.n_sites;

@@ -126,7 +126,7 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
     constexpr int LINES = (REC * 16 + 127) / 128;
     const int pf_group = lane / LINES;
     int pf_delta = 0;           // row offset of the record this lane prefetches
-    bool pf_lane = DICT && NP == 1 && wk.prefetch > 0;
+    bool pf_lane = DICT && NP == 1 && wk.prefetch > 0;  // (the plain kernel streams the matrix: hints only cost it issue slots, measured)
     {
         const int dz = warp % wk.Pz, dy = warp / wk.Pz;
         if (pf_group == 0) pf_delta = M;
@@ -592,14 +592,12 @@ int ell_build(bdg_system *sys) {
 int ell_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    // Measured (profiles/r01/sweep_ell_v1.log): these kernels are latency-bound once the vectors
-    // dominate, so occupancy (24 warps/SM at one panel per warp-row) beats reusing the block
-    // registers for 4 or 8 panels (16 warps/SM) -- concurrent panel groups sweep the lattice in
-    // step and L2 de-duplicates their matrix reads.  Two panels per pass pay off when the matrix
-    // is L2-resident or the rows are long (3-D lattices: more block bytes per record byte).
-    const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;
-    const bool pair = st.panel_width == 8 && st.n_panels >= 2 &&
-                      (e.width >= 6 || matrix_bytes < ((size_t)64 << 20));
+    // One panel per pass, each panel group marching the lattice on its own CTAs: with the marching
+    // traversal and the L1 prefetch this beats sharing the block registers between panels for every
+    // dictionary workload measured (profiles/r01/quickperf_np_v2.log).  The plain kernel on 3-D
+    // lattices (long rows: more block bytes per record byte) still gains from two panels per pass.
+    const bool dict = st.kernel != BDG_KERNEL_ELL;
+    const bool pair = !dict && st.panel_width == 8 && st.n_panels >= 2 && e.width >= 6;
     st.panels_per_group = pair ? 2 : 1;
     st.panel_batch = st.panels_per_group;
     // tuning overrides (development): BDG_ELL_NP in {1,2,4,8}, BDG_ELL_PB in {1,2}
