@@ -117,7 +117,7 @@ enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
  * DICT = the ELL kernel on a block-dictionary copy of the matrix: the distinct 4x4 blocks once, plus a
  *        4-byte code per block.  Lattice Hamiltonians repeat a handful of hopping / on-site blocks
  *        millions of times, so the per-step matrix traffic drops from 260 to 8 bytes per block; the
- *        arithmetic and its order are those of ELL (results are bit-identical).  Chosen when the
+ *        arithmetic and its order are those of ELL (vectors bit-identical; moments too when the grids agree).  Chosen when the
  *        distinct blocks are <= 35 % of all blocks;
  * ELL  = FP64 warp-MMA on the kernel-native fixed-width row format (block rows of <= 8 blocks: every
  *        lattice Hamiltonian), one pass over the matrix serving up to 32 columns;

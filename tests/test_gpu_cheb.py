@@ -488,3 +488,44 @@ def test_boundedness_check_rejects_a_scale_that_is_too_small(gpu_api):
     bad = system.chebyshev_moments(258, vectors=4, seed=1, scale=0.99 * lam)[0::2]
     assert np.all(ok <= ok[0] * (1 + 1e-9))
     assert not np.all(bad <= bad[0] * (1 + 1e-9))
+
+
+# ---- BASELINE.json's full sizes: size-independent properties --------------------------------------
+@pytest.mark.parametrize("cfg", ["C5", "C4"])
+def test_full_size_recursion_properties(cfg):
+    """10^6-site junction (C5) and 64^3 s-wave (C4), 8 stochastic columns: the matrix formats of the
+    step kernel agree (the dictionary kernel's VECTORS are bit-identical to the plain copy's; its dot
+    products are summed over a different partition of the rows -- the grid differs -- so moments agree
+    to rounding; the DFMA variant to 1e-12), runs are bit-reproducible, mu_0 = <x|x> = 4N exactly,
+    |mu_n| <= mu_0, and the recursion is linear: the summed moments equal the sum of the per-column moments."""
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    c = workloads.CONFIGS[cfg]
+    system = b.Hamiltonian(b.CubicLattice(c["shape"]))
+    assert system.fill(*c["build"](c["shape"])) == 0.0
+    n_rows = system.shape[0]
+    scale = system.spectral_bound()
+    runs = {k: system.chebyshev_moments(24, vectors=8, seed=1234, scale=scale, kernel=k) for k in ("ell", "dict", "dict_diag", "auto")}
+    assert system._sys.cheb_format()["kernel"] == "dict_diag"
+    assert rel_err(runs["dict"], runs["ell"]) <= 1e-13
+    assert np.array_equal(runs["auto"], runs["dict_diag"])
+    if cfg == "C4":  # 134 MB per vector set: compare T_n itself after a few steps
+        vecs = {}
+        for k in ("ell", "dict"):
+            system._sys.cheb_begin(n_random=8, seed=1234, scale=scale, kernel=k)
+            system._sys.cheb_steps(5)
+            vecs[k] = system._sys.cheb_vectors(8, 0)
+        assert np.array_equal(vecs["dict"], vecs["ell"])
+        del vecs
+    assert rel_err(runs["dict_diag"], runs["ell"]) <= 1e-12
+    mu = runs["auto"]
+    assert np.array_equal(mu[0], np.full(8, float(n_rows)))
+    assert np.all(np.abs(mu) <= n_rows * (1 + 1e-12))
+    assert np.array_equal(mu, system.chebyshev_moments(24, vectors=8, seed=1234, scale=scale))
+    summed = system.chebyshev_moments(24, vectors=8, seed=1234, scale=scale, summed=True)
+    assert rel_err(summed, mu.sum(axis=1)) <= 1e-13
+    # mu_1 = <x|H|x>/a for Rademacher x: Tr H = 0 for a BdG matrix, so mu_1 is pure sampling noise ~ sqrt(N)
+    assert np.all(np.abs(mu[1]) < 50 * np.sqrt(n_rows))
+    # generic-BSR kernel on the same matrix (no fixed-width copy, no dictionary)
+    assert rel_err(system.chebyshev_moments(24, vectors=8, seed=1234, scale=scale, kernel="dmma"), runs["ell"]) <= 1e-12
