@@ -218,6 +218,8 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout carries the JSON line only
+        os.environ["NCCL_DEBUG"] = os.environ.get("BDG_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = workloads.CONFIGS[args.config]
     shape, cols, K, W = cfg["shape"], args.cols, args.steps, args.warmup
