@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C5")
-    ap.add_argument("--cols", type=int, default=8, help="vector columns per GPU")
+    ap.add_argument("--cols", type=int, default=8, help="vector columns per GPU (weak scaling, the default)")
+    ap.add_argument("--total-cols", type=int, default=0,
+                    help="strong scaling instead: this many columns in total, split evenly over the GPUs (SURVEY 8e: 64)")
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -223,6 +225,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = workloads.CONFIGS[args.config]
     shape, cols, K, W = cfg["shape"], args.cols, args.steps, args.warmup
+    scaling = "weak"
+    if args.total_cols > 0:
+        if args.total_cols % world:
+            raise SystemExit(f"--total-cols {args.total_cols} is not divisible by {world} GPUs")
+        cols, scaling = args.total_cols // world, "strong"
 
     # ---- inputs: Hamiltonian terms as packed arrays in pinned host memory --------------------
     packed = cfg["build"](shape)
@@ -393,7 +400,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": world * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": cfg["label"], "config": args.config, "n_sites": n_sites, "n_blocks": info["n_blocks"],
                    "cols_per_gpu": cols, "parallelism": f"column shards x{world}, matrix replicated",
