@@ -399,7 +399,9 @@ def run_ours(args):
                "assembly_sites_per_s": res["n_sites"] / res["assembly_s"]}
 
     line = {
-        "metric": METRIC, "value": world * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        # weak scaling: every GPU advances its own 8-column job, the job count adds up; strong scaling:
+        # one job of --total-cols columns, a step is done when every shard has done it
+        "metric": METRIC, "value": (world if scaling == "weak" else 1) * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": cfg["label"], "config": args.config, "n_sites": n_sites, "n_blocks": info["n_blocks"],
