@@ -323,7 +323,7 @@ def run_ours(args):
     # The same steps on the uncompressed fixed-width matrix copy (every block read from HBM): shows
     # what the block dictionary buys and how close the plain kernel runs to the HBM roofline.
     plain = None
-    if fmt["kernel"].startswith("dict") and not args.no_plain:
+    if (fmt["kernel"].startswith("dict") or fmt["kernel"] == "pair") and not args.no_plain:
         p_total, p_kernel, _, _, p_fmt = timed_steps("ell")
         plain = {"kernel": "cheb_step_ell (every block from HBM)", "kernel_ms_per_launch": p_kernel / K,
                  "steps_per_s": world * K / (p_total * 1e-3), "matrix_bytes_per_launch": p_fmt["matrix_bytes_per_step"]}
@@ -372,17 +372,23 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     bytes_step = info["bytes_per_step"]
     achieved = bytes_step * K / (kernel_ms * 1e-3) / 1e9
-    moved_step = fmt["matrix_bytes_per_step"] + 192 * n_sites * cols
+    # per step: three vector passes; the pair kernel (two steps per launch) moves four per two steps
+    moved_step = fmt["matrix_bytes_per_step"] + (128 if fmt["kernel"] == "pair" else 192) * n_sites * cols
     moved = moved_step * K / (kernel_ms * 1e-3) / 1e9
-    kernel_name = {"dict": "cheb_step_ell<DICT> (block-dictionary matrix)",
+    step_launches = max(launches - 1, 1)   # `launches` also counts the moment read-out kernel
+    steps_per_launch = K / step_launches
+    kernel_name = {"pair": "cheb_pair_step (two steps per launch: block-dictionary matrix, T_n / T_{n-1} planes staged by "
+                           "TMA bulk copies, T_{n+1} kept in shared memory)",
+                   "dict": "cheb_step_ell<DICT> (block-dictionary matrix)",
                    "dict_diag": "cheb_step_ell<DICT,DIAG> (block-dictionary matrix, real-diagonal hopping blocks by DFMA)",
                    "ell": "cheb_step_ell",
                    "dmma": "cheb_step_dmma", "fma": "cheb_step_fma"}.get(fmt["kernel"], fmt["kernel"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(f"{args.config}_k{cols}_{fmt['kernel']}"), "peak_source": peak_src,
-                "kernel": kernel_name, "algorithmic_bytes_per_launch": bytes_step,
-                "kernel_ms_per_launch": kernel_ms / K, "matrix_format": fmt["kernel"],
-                "distinct_blocks": fmt["distinct_blocks"], "moved_bytes_per_launch": moved_step,
+                "kernel": kernel_name, "steps_per_launch": steps_per_launch,
+                "algorithmic_bytes_per_launch": bytes_step * steps_per_launch,
+                "kernel_ms_per_launch": kernel_ms / step_launches, "matrix_format": fmt["kernel"],
+                "distinct_blocks": fmt["distinct_blocks"], "moved_bytes_per_launch": moved_step * steps_per_launch,
                 "moved_GBps": moved, "moved_frac": moved / peak}
     if plain is not None:
         plain["achieved"] = bytes_step / (plain["kernel_ms_per_launch"] * 1e-3) / 1e9

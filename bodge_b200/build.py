@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbdg.so")
-SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu", "observables.cu"]
+SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu", "cheb_pair.cu", "observables.cu"]
 
 
 def nvcc_path() -> str:

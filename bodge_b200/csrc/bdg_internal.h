@@ -75,6 +75,14 @@ struct RowWalk {
     int prefetch = 0;            // rows ahead (a multiple of Ly*Lz) whose records are prefetched into L1; 0 = off
 };
 
+// Item grid of the two-steps-per-pass kernel (cheb_pair.cu): x-planes of M sites, cut into patches of
+// P owned sites; an item = (patch, segment of seg_len consecutive x), handed out segment-major.
+struct PairWalk {
+    int Lx = 1, M = 1;
+    int P = 1, n_patches = 1;
+    int seg_len = 1, n_segs = 1, n_items = 1;
+};
+
 // ---- Chebyshev state ----------------------------------------------------------------------
 struct ChebState {
     bool active = false;
@@ -86,8 +94,13 @@ struct ChebState {
     int32_t steps_done = 0;   // recursion steps after T_1 (T_{steps_done+1} is current)
     int32_t dot_capacity = 0; // steps for which dot storage exists
     // Vectors: [panel][site][col_in_panel][alpha] complex128; cur = T_n, prev = T_{n-1}.
-    DevBuf vec[2];
-    int cur = 0;
+    // The pair kernel writes T_{n+1}, T_{n+2} into the two buffers that hold neither (vec[2], vec[3]
+    // exist only then); the single-step kernels overwrite prev in place.
+    DevBuf vec[4];
+    int cur = 0, prev = 1;
+    bool pair = false;         // two steps per launch whenever two or more remain (cheb_pair.cu)
+    int pair_grid_x = 0;
+    PairWalk pair_walk;
     // dots[(step * 2 + which) * n_panels * PW + panel * PW + c]; which 0 = <T_n,T_n>, 1 = <T_{n+1},T_n>
     DevBuf dots;
     DevBuf partials;  // per-CTA partial dot products of the step in flight
@@ -120,6 +133,10 @@ struct EllDev {
     bool diag_usable = false;  // every block outside slot 0 is real and diagonal: dtab[n_unique][4] holds the diagonals
     int64_t n_unique = 0;
     DevBuf code, table, dtab;
+    // Two-steps-per-pass kernel (cheb_pair.cu): dictionary format + nearest-neighbour stencil on a
+    // lattice whose x-planes are one-dimensional (pair_M sites per plane).
+    bool pair_usable = false;
+    int pair_M = 0;
     DevBuf tmp_keys, tmp_rep, tmp_where, tmp_dense;  // hash-table scratch of the dictionary build (kept for rebuilds)
 };
 
@@ -162,5 +179,10 @@ int ell_build(bdg_system *sys);                    // (re)build sys->ell from sy
 int ell_configure(bdg_system *sys);                // pick panels_per_group / grid for the current ChebState
 int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
 void ell_release(bdg_system *sys);
+
+// cheb_pair.cu
+int pair_probe(bdg_system *sys);      // sets sys->ell.pair_usable / pair_M (called by ell_build)
+int pair_configure(bdg_system *sys);  // patch / segment plan and grid for the current ChebState
+int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -22,12 +22,16 @@
 // because it removes the FP64 issue/broadcast overhead a scalar formulation has, not
 // to chase flops.  cheb_step_fma is the scalar-FMA formulation of the same step (A/B reference).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
 
 namespace {
+
+constexpr bool kAutoPairDefault = false;  // flipped once the pair kernel is measured ahead (profiles/)
 
 
 // ---- the fused step: FP64 warp-MMA formulation --------------------------------------------------
@@ -372,6 +376,12 @@ StepKernel pick_kernel(int kernel, int pw, bool first, int max_row) {
     }
 }
 
+// AUTO prefers the two-steps-per-pass kernel wherever it applies (BDG_AUTO_PAIR=0 turns that off).
+bool auto_pair_enabled() {
+    const char *v = getenv("BDG_AUTO_PAIR");
+    return v && *v ? atoi(v) != 0 : kAutoPairDefault;
+}
+
 int launch_step(bdg_system *sys, bool first) {
     ChebState &st = sys->cheb;
     const BsrDev &m = sys->packed;
@@ -379,10 +389,10 @@ int launch_step(bdg_system *sys, bool first) {
     const int stride = st.n_panels * st.panel_width;
     double *dots_step = st.dots.as<double>() + (size_t)slot * 2 * stride;
     const double2 *x_cur = st.vec[st.cur].as<double2>();
-    double2 *x_io = st.vec[st.cur ^ 1].as<double2>();
+    double2 *x_io = st.vec[st.prev].as<double2>();
     if (st.kernel == BDG_KERNEL_ELL || st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG) {
         BDG_TRY(ell_launch_step(sys, first, x_cur, x_io, dots_step));
-        st.cur ^= 1;
+        std::swap(st.cur, st.prev);
         st.launches += 1;
         return BDG_OK;
     }
@@ -394,7 +404,24 @@ int launch_step(bdg_system *sys, bool first) {
                                           first ? 0.0 : 1.0, st.partials.as<double>(), st.tickets.as<unsigned>(),
                                           dots_step, st.n_panels);
     BDG_CUDA(cudaGetLastError());
-    st.cur ^= 1;
+    std::swap(st.cur, st.prev);
+    st.launches += 1;
+    return BDG_OK;
+}
+
+// Two steps in one launch (cheb_pair.cu): T_{n+1}, T_{n+2} go to the two buffers holding neither
+// T_n nor T_{n-1}; dot products of steps n and n+1.
+int launch_pair(bdg_system *sys) {
+    ChebState &st = sys->cheb;
+    const int slot = st.steps_done + 1;
+    const int stride = st.n_panels * st.panel_width;
+    int out[2], n_out = 0;
+    for (int b = 0; b < 4; ++b)
+        if (b != st.cur && b != st.prev) out[n_out++] = b;
+    BDG_TRY(pair_launch(sys, st.vec[st.prev].ptr, st.vec[st.cur].ptr, st.vec[out[0]].ptr, st.vec[out[1]].ptr,
+                        st.dots.as<double>() + (size_t)slot * 2 * stride));
+    st.prev = out[0];
+    st.cur = out[1];
     st.launches += 1;
     return BDG_OK;
 }
@@ -427,8 +454,7 @@ void cheb_deactivate(bdg_system *sys) {
 void cheb_release(bdg_system *sys) {
     ChebState &st = sys->cheb;
     cudaStreamSynchronize(sys->stream);
-    dev_free(sys, st.vec[0]);
-    dev_free(sys, st.vec[1]);
+    for (DevBuf &v : st.vec) dev_free(sys, v);
     dev_free(sys, st.dots);
     dev_free(sys, st.partials);
     dev_free(sys, st.tickets);
@@ -451,10 +477,20 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_DICT_DIAG, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_PAIR, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
-    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT || kernel == BDG_KERNEL_DICT_DIAG) {
+    bool pair = false;
+    if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT || kernel == BDG_KERNEL_DICT_DIAG ||
+        kernel == BDG_KERNEL_PAIR) {
         BDG_TRY(ell_build(sys));
+        // The pair kernel works on 8-column panels of the dictionary format; single leftover steps
+        // (and T_1) run on the single-step dictionary kernel of the same format.
+        const bool pair_ok = sys->ell.pair_usable && n_cols >= 5;
+        BDG_REQUIRE(kernel != BDG_KERNEL_PAIR || pair_ok,
+                    "the two-steps-per-pass kernel needs >= 5 columns and a block dictionary on a lattice with "
+                    "one-dimensional x-planes and an open nearest-neighbour stencil");
+        pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && pair_ok && auto_pair_enabled());
+        if (kernel == BDG_KERNEL_PAIR) kernel = BDG_KERNEL_AUTO;
         BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
                     "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");
         BDG_REQUIRE(kernel != BDG_KERNEL_DICT || sys->ell.dict_usable,
@@ -483,6 +519,8 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     st.scale = scale;
     st.steps_done = 0;
     st.cur = 0;
+    st.prev = 1;
+    st.pair = pair;
     st.dot_capacity = (int)(st.dots.bytes / ((size_t)2 * st.n_panels * st.panel_width * sizeof(double)));
 
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
@@ -502,10 +540,13 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
         st.n_groups = st.n_panels;
     }
 
+    st.pair_grid_x = 0;
+    if (st.pair) BDG_TRY(pair_configure(sys));
+
     const size_t vec_elems = (size_t)st.n_panels * n * st.panel_width * 4;
-    BDG_TRY(dev_alloc(sys, st.vec[0], vec_elems * sizeof(double2)));
-    BDG_TRY(dev_alloc(sys, st.vec[1], vec_elems * sizeof(double2)));
-    BDG_TRY(dev_alloc(sys, st.partials, (size_t)st.n_panels * st.grid_x * 16 * sizeof(double)));
+    for (int b = 0; b < (st.pair ? 4 : 2); ++b) BDG_TRY(dev_alloc(sys, st.vec[b], vec_elems * sizeof(double2)));
+    BDG_TRY(dev_alloc(sys, st.partials,
+                      (size_t)st.n_panels * std::max(st.grid_x, st.pair_grid_x) * (st.pair ? 32 : 16) * sizeof(double)));
     BDG_TRY(dev_alloc(sys, st.tickets, (size_t)st.n_panels * sizeof(unsigned)));
     BDG_CUDA(cudaMemsetAsync(st.tickets.ptr, 0, (size_t)st.n_panels * sizeof(unsigned), sys->stream));
     BDG_TRY(ensure_dot_capacity(sys, 1024));
@@ -543,9 +584,16 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
         BDG_CUDA(cudaStreamSynchronize(sys->stream));
         BDG_CUDA(cudaEventRecord(e0, sys->stream));
     }
-    for (int s = 0; s < n_steps; ++s) {
-        BDG_TRY(launch_step(sys, false));
-        st.steps_done += 1;
+    for (int s = 0; s < n_steps;) {
+        if (st.pair && n_steps - s >= 2) {
+            BDG_TRY(launch_pair(sys));
+            st.steps_done += 2;
+            s += 2;
+        } else {
+            BDG_TRY(launch_step(sys, false));
+            st.steps_done += 1;
+            s += 1;
+        }
     }
     if (elapsed_ms) {
         BDG_CUDA(cudaEventRecord(e1, sys->stream));
@@ -615,7 +663,7 @@ extern "C" int bdg_cheb_vectors(bdg_t *sys, int which, double *out) {
     DevBuf tmp;
     BDG_TRY(dev_alloc(sys, tmp, count * sizeof(double2)));
     unpack_vectors<<<(unsigned)ceil_div((int64_t)count, kThreads), kThreads, 0, sys->stream>>>(
-        st.vec[st.cur ^ which].as<double2>(), (int)m.n_sites, st.panel_width, st.n_cols, tmp.as<double2>());
+        st.vec[which ? st.prev : st.cur].as<double2>(), (int)m.n_sites, st.panel_width, st.n_cols, tmp.as<double2>());
     cudaError_t err = cudaMemcpyAsync(out, tmp.ptr, count * sizeof(double2), cudaMemcpyDeviceToHost, sys->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(sys->stream);
     dev_free(sys, tmp);
@@ -644,10 +692,12 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
     const BsrDev &m = sys->packed;
     const EllDev &e = sys->ell;
-    if (kernel) *kernel = st.kernel;
+    if (kernel) *kernel = st.pair ? BDG_KERNEL_PAIR : st.kernel;
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
-        if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
+        if (st.pair)  // one pass over the codes and indices serves two steps
+            *matrix_bytes_per_step = e.n_sites * e.width * 4 + e.n_unique * 256;
+        else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_ELL)
             *matrix_bytes_per_step = e.n_sites * e.width * 260;

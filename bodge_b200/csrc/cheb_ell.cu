@@ -556,6 +556,7 @@ int ell_build(bdg_system *sys) {
     e.usable = false;
     e.dict_usable = false;
     e.diag_usable = false;
+    e.pair_usable = false;
     e.n_unique = 0;
     e.n_sites = n;
     if (n > 0) {
@@ -582,6 +583,7 @@ int ell_build(bdg_system *sys) {
             BDG_CUDA(cudaGetLastError());
             e.usable = true;
             BDG_TRY(dict_build(sys));
+            BDG_TRY(pair_probe(sys));
         }
     }
     e.valid = true;

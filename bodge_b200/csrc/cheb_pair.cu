@@ -1,0 +1,470 @@
+// Two Chebyshev steps per pass over the vectors ("pair step", SURVEY 8f-4: temporal blocking).
+//
+//     T_{n+1} = 2 H~ T_n - T_{n-1},     T_{n+2} = 2 H~ T_{n+1} - T_n
+//
+// in ONE launch, on the block-dictionary matrix format of cheb_ell.cu.  A single-step kernel moves
+// three vector passes per step (read T_n, read T_{n-1}, write T_{n+1}); this one moves four per TWO
+// steps (read T_{n-1}, T_n; write T_{n+1}, T_{n+2}) because T_{n+1} never has to come back from HBM:
+// it is consumed out of shared memory.  With the matrix already out of the HBM stream (dictionary
+// format) that is the only way past the one-pass roofline of the step.
+//
+// Geometry.  Lattices whose x-planes are one-dimensional (Lz = 1 or Ly = 1; M = sites per plane).
+// The plane is cut into patches of P owned sites; a CTA marches one patch along a segment of x:
+//
+//   iteration x:  [A] T_{n+1}(x, y) for the P owned sites AND one halo site on either side,
+//                     from T_n planes x-1, x, x+1 (P + 4 sites each) and T_{n-1} plane x (P + 2),
+//                     all staged in shared memory by bulk async copies (TMA, cp.async.bulk, one
+//                     contiguous 17 KB run per plane, two planes ahead, completion on an mbarrier);
+//                     the result goes to a shared-memory ring (4 planes) and, for owned sites of
+//                     owned planes, to HBM;
+//                 __syncthreads
+//                 [B] T_{n+2}(x-1, y) for the owned sites from the ring's planes x-2, x-1, x
+//                     (the T_n record of the site itself is still in registers from [A](x-1)).
+//
+// The halo T_{n+1} values (one site either side in y, one plane either side of the segment in x)
+// are recomputed, not exchanged: (P+2)/P x (len+2)/len redundant work on sub-step [A], no
+// inter-CTA dependency, deterministic.  Because a neighbouring CTA may still need T_{n-1} / T_n of
+// a site after its owner has produced T_{n+1} / T_{n+2} there, the outputs go to two further
+// buffers (four vector buffers in rotation) instead of in place.
+//
+// Arithmetic per row is exactly that of cheb_step_ell<.., DICT, DIAG> (same fragments, same order,
+// same update expression): the vectors are bit-identical to the single-step dictionary kernels';
+// the dot products are summed over a different partition of the rows (agree to rounding).
+#include <algorithm>
+#include <cstdlib>
+
+#include "bdg_internal.h"
+#include "cheb_device.cuh"
+
+namespace {
+
+constexpr int kRecBytes = 512;  // one site record at PW = 8: 8 columns x 4 components x complex128
+constexpr int kRing = 4;        // planes per shared-memory ring (power of two)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// One contiguous run global -> shared through the TMA unit (SASS UBLKCP); bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ double2 lds_rec(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_rec(uint32_t addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void ld_table_pred(double &v, const double *p, unsigned take) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(v) : "l"(p), "r"(take));
+}
+
+// B fragments of a row (cheb_ell.cu: DICT / DIAG): reloaded only when a code differs from the held one.
+template <int CH, bool DIAG>
+__device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[CH], const double *__restrict__ table,
+                                               const double *__restrict__ dtab, int lane) {
+    const unsigned changed = __ballot_sync(kFull, jv != jheld) >> 8;
+    if (changed) {
+        jheld = jv;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int code = __shfl_sync(kFull, jv, 8 + u);
+            const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : table + (size_t)code * 32 + lane;
+            ld_table_pred(keep[u], entry, changed >> u & 1u);
+        }
+    }
+}
+
+// y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell.
+template <int CH, bool DIAG>
+__device__ __forceinline__ void row_product(const double2 (&xv)[CH], const double (&bop)[CH], double &yr, double &yi) {
+    double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
+#pragma unroll
+    for (int u = 0; u < (DIAG ? 1 : CH); ++u) {
+        dmma_8x8x4(a10, a11, xv[u].x, bop[u]);
+        dmma_8x8x4(a20, a21, xv[u].y, bop[u]);
+    }
+    yr = a10 - a21;
+    yi = a11 + a20;
+    if (DIAG) {
+#pragma unroll
+        for (int u = 1; u < CH; ++u) {
+            yr = fma(bop[u], xv[u].x, yr);
+            yi = fma(bop[u], xv[u].y, yi);
+        }
+    }
+}
+
+// NW warps per CTA, S sites per warp and plane: W = NW * S sites per plane in sub-step [A]
+// (P <= W - 2 of them owned).  Dynamic shared memory: kRing x ((W + 2) + W + W) records + barriers.
+template <int CH, bool DIAG, int NW, int S>
+__global__ void __launch_bounds__(NW * 32, 16 / NW)
+cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode, const double *__restrict__ table,
+               const double *__restrict__ dtab, const double2 *__restrict__ xa /* T_{n-1} */,
+               const double2 *__restrict__ xb /* T_n */, double2 *__restrict__ xc /* T_{n+1} */,
+               double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels, double alpha, double beta,
+               double *__restrict__ partials, unsigned *__restrict__ tickets, double *__restrict__ dots_step,
+               const PairWalk wk) {
+    constexpr int W = NW * S;
+    constexpr uint32_t PLANE_N = (W + 2) * kRecBytes, PLANE_W = W * kRecBytes;
+    extern __shared__ __align__(128) unsigned char pair_smem[];
+    const uint32_t sTn = smem_u32(pair_smem);         // T_n planes, local site l2 = y - (y0 - 2)
+    const uint32_t sTp = sTn + kRing * PLANE_N;       // T_{n-1} planes, local site l = y - (y0 - 1)
+    const uint32_t sT1 = sTp + kRing * PLANE_W;       // T_{n+1} planes (computed here), local site l
+    const uint32_t sBar = sT1 + kRing * PLANE_W;      // one mbarrier per ring slot
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int panel = blockIdx.y;
+    const size_t pbase = (size_t)panel * n_sites * 32;
+    const double2 *ta = xa + pbase, *tb = xb + pbase;
+    double2 *tc = xc + pbase, *td = xd + pbase;
+    // Per-row index fetch: lanes 0..CH-1 read the slot's block column, lanes 8..8+CH-1 its code.
+    const int32_t *islot = lane >= 8 ? ccode - 8 : cidx;
+    const bool ilane = (lane & 7) < CH && lane < 16;
+    const uint32_t lane16 = (uint32_t)lane * 16u;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < kRing; ++r) mbar_init(sBar + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phases = 0;  // bit r = parity of the next completion of ring slot r
+
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    double keep[S][CH];
+    int jheld[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        jheld[s] = -1;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) keep[s][u] = 0.0;
+    }
+
+    for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
+        const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
+        const int y0 = patch * wk.P, x0 = seg * wk.seg_len, x1 = min(wk.Lx, x0 + wk.seg_len);
+        const int xlo = max(0, x0 - 1), xhi = min(wk.Lx, x1 + 1);    // planes of sub-step [A]
+        const int tlo = max(0, xlo - 1), thi = min(wk.Lx, xhi + 1);  // T_n planes they read
+        const int nlo = max(0, y0 - 2), nhi = min(wk.M, y0 + wk.P + 2);  // in-plane run of T_n
+        const int plo = max(0, y0 - 1), phi = min(wk.M, y0 + wk.P + 1);  // ... of T_{n-1}
+        int issued = tlo, waited = tlo;
+
+        // Plane q -> ring slot q % kRing: T_n always, T_{n-1} when [A] runs on it; one barrier phase.
+        auto issue_upto = [&](int last) {
+            for (; issued <= last && issued < thi; ++issued) {
+                if (threadIdx.x == 0) {
+                    const int q = issued, r = q & (kRing - 1);
+                    const bool with_prev = q >= xlo && q < xhi;
+                    const uint32_t nbytes = (uint32_t)(nhi - nlo) * kRecBytes;
+                    const uint32_t pbytes = with_prev ? (uint32_t)(phi - plo) * kRecBytes : 0u;
+                    mbar_expect_tx(sBar + 8 * r, nbytes + pbytes);
+                    bulk_g2s(sTn + r * PLANE_N + (uint32_t)(nlo - (y0 - 2)) * kRecBytes, tb + ((size_t)q * wk.M + nlo) * 32,
+                             nbytes, sBar + 8 * r);
+                    if (with_prev)
+                        bulk_g2s(sTp + r * PLANE_W + (uint32_t)(plo - (y0 - 1)) * kRecBytes,
+                                 ta + ((size_t)q * wk.M + plo) * 32, pbytes, sBar + 8 * r);
+                }
+            }
+        };
+
+        __syncthreads();  // every warp is done with the previous item's planes
+        issue_upto(xlo + 2);
+
+        int yy[S], jvA[S], jvB[S];
+        bool exists[S], owned[S];
+        double2 tnA[S], tnB[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int l = warp + NW * s;
+            yy[s] = y0 - 1 + l;
+            exists[s] = l < wk.P + 2 && yy[s] >= 0 && yy[s] < wk.M;
+            owned[s] = exists[s] && l >= 1 && l <= wk.P;
+            jvA[s] = jvB[s] = 0;
+            tnA[s] = tnB[s] = make_double2(0.0, 0.0);
+            if (exists[s] && ilane) jvA[s] = __ldg(islot + ((size_t)xlo * wk.M + yy[s]) * CH + lane);
+        }
+
+        for (int x = xlo; x <= x1; ++x) {
+            // Plane x+2 replaces plane x-2, last read by [A](x-1): every warp finished that before the
+            // barrier of iteration x-1, which this thread has passed.
+            if (x > xlo) issue_upto(x + 2);
+            for (; waited <= x + 1 && waited < thi; ++waited) {
+                const int r = waited & (kRing - 1);
+                mbar_wait(sBar + 8 * r, (phases >> r) & 1u);
+                phases ^= 1u << r;
+            }
+            const bool do_a = x < xhi;
+            int jnext[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                jnext[s] = 0;
+                if (do_a && x + 1 < xhi && exists[s] && ilane) jnext[s] = __ldg(islot + ((size_t)(x + 1) * wk.M + yy[s]) * CH + lane);
+            }
+            if (do_a) {
+                const bool store = x >= x0 && x < x1;
+                const uint32_t slot = (uint32_t)(x & (kRing - 1));
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (!exists[s]) continue;  // warp-uniform
+                    const int l = warp + NW * s;
+                    const int row = x * wk.M + yy[s];
+                    hold_fragments<CH, DIAG>(jvA[s], jheld[s], keep[s], table, dtab, lane);
+                    // lane u < CH: where the record of slot u's block column sits in the T_n ring
+                    const int dj = jvA[s] - row;
+                    const int dxp = (dj >= wk.M) - (dj <= -wk.M);
+                    const int dl = dj - dxp * wk.M;
+                    const uint32_t mine = (uint32_t)((x + dxp) & (kRing - 1)) * PLANE_N + (uint32_t)(l + 1 + dl) * kRecBytes;
+                    double2 xv[CH];
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) xv[u] = lds_rec(sTn + __shfl_sync(kFull, mine, u) + lane16);
+                    const double2 pv = lds_rec(sTp + slot * PLANE_W + (uint32_t)l * kRecBytes + lane16);
+                    double yr, yi;
+                    row_product<CH, DIAG>(xv, keep[s], yr, yi);
+                    const double2 out = make_double2(alpha * yr - beta * pv.x, alpha * yi - beta * pv.y);
+                    sts_rec(sT1 + slot * PLANE_W + (uint32_t)l * kRecBytes + lane16, out);
+                    tnA[s] = xv[0];  // slot 0 is the row's own record
+                    if (store && owned[s]) {
+                        tc[(size_t)row * 32 + lane] = out;
+                        d0 += xv[0].x * xv[0].x + xv[0].y * xv[0].y;
+                        d1 += out.x * xv[0].x + out.y * xv[0].y;
+                    }
+                }
+            }
+            __syncthreads();  // T_{n+1}(x) complete in the ring
+            if (x - 1 >= x0) {
+                const int xb1 = x - 1;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (!owned[s]) continue;  // warp-uniform
+                    const int l = warp + NW * s;
+                    const int row = xb1 * wk.M + yy[s];
+                    hold_fragments<CH, DIAG>(jvB[s], jheld[s], keep[s], table, dtab, lane);
+                    const int dj = jvB[s] - row;
+                    const int dxp = (dj >= wk.M) - (dj <= -wk.M);
+                    const int dl = dj - dxp * wk.M;
+                    const uint32_t mine = (uint32_t)((xb1 + dxp) & (kRing - 1)) * PLANE_W + (uint32_t)(l + dl) * kRecBytes;
+                    double2 xv[CH];
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) xv[u] = lds_rec(sT1 + __shfl_sync(kFull, mine, u) + lane16);
+                    double yr, yi;
+                    row_product<CH, DIAG>(xv, keep[s], yr, yi);
+                    const double2 out = make_double2(alpha * yr - beta * tnB[s].x, alpha * yi - beta * tnB[s].y);
+                    td[(size_t)row * 32 + lane] = out;
+                    d2 += xv[0].x * xv[0].x + xv[0].y * xv[0].y;
+                    d3 += out.x * xv[0].x + out.y * xv[0].y;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                jvB[s] = jvA[s];
+                tnB[s] = tnA[s];
+                jvA[s] = jnext[s];
+            }
+        }
+    }
+
+    // ---- the four dot products of the two steps: quad -> warp -> CTA -> last CTA, fixed order ----
+    d0 += __shfl_xor_sync(kFull, d0, 1);
+    d1 += __shfl_xor_sync(kFull, d1, 1);
+    d2 += __shfl_xor_sync(kFull, d2, 1);
+    d3 += __shfl_xor_sync(kFull, d3, 1);
+    d0 += __shfl_xor_sync(kFull, d0, 2);
+    d1 += __shfl_xor_sync(kFull, d1, 2);
+    d2 += __shfl_xor_sync(kFull, d2, 2);
+    d3 += __shfl_xor_sync(kFull, d3, 2);
+    __syncthreads();  // the rings are dead: reuse them as reduction scratch
+    double *red = reinterpret_cast<double *>(pair_smem);  // [NW][4][8], then comb [NW][32] behind it
+    double *comb = red + NW * 32;
+    __shared__ bool is_last;
+    if ((lane & 3) == 0) {
+        const int col = lane >> 2;
+        red[(warp * 4 + 0) * 8 + col] = d0;
+        red[(warp * 4 + 1) * 8 + col] = d1;
+        red[(warp * 4 + 2) * 8 + col] = d2;
+        red[(warp * 4 + 3) * 8 + col] = d3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[w * 32 + threadIdx.x];
+        partials[(size_t)(panel * gridDim.x + blockIdx.x) * 32 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    {
+        double s = 0.0;
+        for (unsigned b = warp; b < gridDim.x; b += NW) s += __ldcg(&partials[(size_t)(panel * gridDim.x + b) * 32 + lane]);
+        comb[warp * 32 + lane] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < NW; ++g) t += comb[g * 32 + threadIdx.x];
+        // slot = which * 8 + column; which = (step within the pair) * 2 + (0: <T,T>, 1: <T',T>)
+        dots_step[(size_t)(threadIdx.x >> 3) * n_panels * 8 + panel * 8 + (threadIdx.x & 7)] = t;
+    }
+    if (threadIdx.x == 0) tickets[panel] = 0u;
+}
+
+// *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its four
+// nearest neighbours in the (x, in-plane) grid, without wrap-around.
+__global__ void __launch_bounds__(256)
+pair_check(int64_t n_slots, int width, int M, const int32_t *__restrict__ cidx, int *__restrict__ bad) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slots) return;
+    const int row = (int)(t / width), d = cidx[t] - row, m = row % M;
+    const bool ok = d == 0 || d == M || d == -M || (d == 1 && m != M - 1) || (d == -1 && m != 0);
+    if (!ok) *bad = 1;
+}
+
+using PairKernel = void (*)(const int32_t *, const int32_t *, const double *, const double *, const double2 *,
+                            const double2 *, double2 *, double2 *, int, int, double, double, double *, unsigned *,
+                            double *, const PairWalk);
+
+template <int NW, int S> PairKernel pick_pair_shape(bool diag, int width) {
+    if (diag) {
+        switch (width) {
+            case 3: return cheb_pair_step<3, true, NW, S>;
+            case 4: return cheb_pair_step<4, true, NW, S>;
+            default: return cheb_pair_step<5, true, NW, S>;
+        }
+    }
+    switch (width) {
+        case 3: return cheb_pair_step<3, false, NW, S>;
+        case 4: return cheb_pair_step<4, false, NW, S>;
+        default: return cheb_pair_step<5, false, NW, S>;
+    }
+}
+
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
+
+struct PairShape {
+    int warps, sites;  // NW, S
+    PairKernel kernel;
+    size_t smem;
+};
+
+PairShape pair_shape(bool diag, int width) {
+    PairShape s;
+    if (env_int("BDG_PAIR_WARPS", 16) <= 8) {
+        s.warps = 8, s.sites = 2;
+        s.kernel = pick_pair_shape<8, 2>(diag, width);
+    } else {
+        s.warps = 16, s.sites = 2;
+        s.kernel = pick_pair_shape<16, 2>(diag, width);
+    }
+    const int W = s.warps * s.sites;
+    s.smem = (size_t)kRing * ((W + 2) + 2 * W) * kRecBytes + 64;
+    return s;
+}
+
+}  // namespace
+
+// Does the current fixed-width copy qualify?  (dictionary built, one-dimensional x-planes, nearest-
+// neighbour stencil without wrap-around, rows of <= 5 blocks)
+int pair_probe(bdg_system *sys) {
+    EllDev &e = sys->ell;
+    e.pair_usable = false;
+    e.pair_M = 0;
+    if (!e.usable || !e.dict_usable || e.width > 5 || e.width < 3) return BDG_OK;
+    const int Lx = sys->cubic[0], Ly = sys->cubic[1], Lz = sys->cubic[2];
+    if ((int64_t)Lx * Ly * Lz != e.n_sites) return BDG_OK;
+    const int M = Lz == 1 ? Ly : (Ly == 1 ? Lz : 0);
+    if (M < 3 || Lx < 3) return BDG_OK;
+    BDG_TRY(ensure_scratch(sys, 2, 64));
+    int *bad = sys->scratch_i32[2].as<int>();
+    BDG_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), sys->stream));
+    const int64_t n_slots = e.n_sites * e.width;
+    pair_check<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(n_slots, e.width, M, e.idx.as<int32_t>(), bad);
+    BDG_CUDA(cudaGetLastError());
+    int host = 1;
+    BDG_CUDA(cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+    BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    e.pair_usable = host == 0;
+    e.pair_M = M;
+    return BDG_OK;
+}
+
+// Patch size, segment length and grid for the current recursion.
+int pair_configure(bdg_system *sys) {
+    ChebState &st = sys->cheb;
+    const EllDev &e = sys->ell;
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, e.width);
+    BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
+    int per_sm = 1;
+    BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
+    per_sm = std::max(per_sm, 1);
+    const int64_t slots = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_panels);
+    PairWalk &w = st.pair_walk;
+    w.Lx = sys->cubic[0];
+    w.M = e.pair_M;
+    const int p_max = shape.warps * shape.sites - 2;
+    const int n_patches_min = (int)ceil_div(w.M, p_max);
+    w.P = (int)ceil_div(w.M, n_patches_min);  // balanced patches
+    w.P = std::max(1, std::min(env_int("BDG_PAIR_P", w.P), p_max));
+    w.n_patches = (int)ceil_div(w.M, w.P);
+    // Segment length: every item recomputes one plane of T_{n+1} on either side of its segment and
+    // starts with a cold pipeline (about two more plane times); many items balance the CTAs.
+    double best = -1.0;
+    const int forced = env_int("BDG_PAIR_SEG", 0);
+    for (int n_seg = 1; n_seg <= std::max(1, w.Lx / 4); ++n_seg) {
+        const int len = forced > 0 ? std::min(forced, w.Lx) : (int)ceil_div(w.Lx, n_seg);
+        const int64_t segs = ceil_div(w.Lx, len);
+        const int64_t items = (int64_t)w.n_patches * segs;
+        const double balance = (double)items / (double)(ceil_div(items, slots) * slots);
+        const double score = balance * len / (len + 4.0);
+        if (score > best) {
+            best = score;
+            w.seg_len = len;
+            w.n_segs = (int)segs;
+            w.n_items = (int)items;
+        }
+        if (forced > 0) break;
+    }
+    st.pair_grid_x = (int)std::min<int64_t>(slots, w.n_items);
+    return BDG_OK;
+}
+
+// T_{n+1} -> x_next1, T_{n+2} -> x_next2 and the dot products of both steps (dots_step: 4 rows).
+int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step) {
+    ChebState &st = sys->cheb;
+    const EllDev &e = sys->ell;
+    const bool diag = st.kernel == BDG_KERNEL_DICT_DIAG;
+    const PairShape shape = pair_shape(diag, e.width);
+    dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
+    shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
+        e.idx.as<int32_t>(), e.code.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(),
+        static_cast<const double2 *>(x_prev), static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1),
+        static_cast<double2 *>(x_next2), (int)e.n_sites, st.n_panels, 2.0 / st.scale, 1.0, st.partials.as<double>(),
+        st.tickets.as<unsigned>(), dots_step, st.pair_walk);
+    BDG_CUDA(cudaGetLastError());
+    return BDG_OK;
+}

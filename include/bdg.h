@@ -111,6 +111,11 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
 /* AUTO = DICT_DIAG, else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+ * PAIR = two recursion steps per launch on the DICT / DICT_DIAG format: T_{n+1} is consumed out of shared
+ *        memory instead of coming back from HBM, so two steps move four vector passes instead of six.  Needs
+ *        >= 5 columns and a lattice with one-dimensional x-planes (Lz = 1 or Ly = 1) whose stored blocks form
+ *        an open nearest-neighbour stencil; vectors bit-identical to DICT / DICT_DIAG.  T_1 and an odd
+ *        leftover step run on the single-step kernel of the same format;
  * DICT_DIAG = DICT for matrices whose blocks off the lattice diagonal are all real and diagonal (hopping
  *        -t sigma_0 / m sigma_3 without pairing on the bonds): those blocks cost two DFMA instead of two
  *        FP64 MMAs.  Same sums in a different rounding order than DICT / ELL (agrees to ~1e-15);
@@ -125,7 +130,8 @@ enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
  * FMA  = scalar formulation (A/B reference); SIMPLE / CHUNKED = unpipelined DMMA with wavefront /
  *        per-CTA-chunk row traversal (tuning references). */
 enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_ELL = 3,
-       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6, BDG_KERNEL_DICT_DIAG = 7 };
+       BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6, BDG_KERNEL_DICT_DIAG = 7,
+       BDG_KERNEL_PAIR = 8 };
 
 /* Start a recursion on n_cols start vectors resident on this GPU.
  *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)

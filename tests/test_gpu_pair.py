@@ -1,0 +1,160 @@
+"""The two-steps-per-pass Chebyshev kernel (kernel="pair", csrc/cheb_pair.cu; SURVEY 8f-4 temporal
+blocking): T_{n+1} and T_{n+2} in one launch, T_{n+1} consumed out of shared memory.
+
+Its row arithmetic is that of the single-step dictionary kernels, so the VECTORS must be bit-identical
+to theirs for every patch / segment decomposition (halo values are recomputed, never exchanged); the
+dot products are summed over another partition of the rows and agree to rounding; against the oracle
+(scipy bsr_matvecs recursion) the moments hold the 1e-10 of BASELINE.json.
+"""
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import bdg_oracle as orc
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+SYSTEMS = {
+    # tag: (builder, hopping blocks real-diagonal -> the pair kernel runs its DFMA variant)
+    "readme_24_16_1": (lambda api: cases.readme_swave(api, (24, 16, 1)), True),
+    "junction_30_40_1": (lambda api: cases.junction(api, (30, 40, 1)), True),      # two patches at P = 30
+    "junction_9_1_67": (lambda api: cases.junction(api, (9, 1, 67)), True),        # planes along z, three patches
+    "dwave_13_35_1": (lambda api: cases.dwave_rashba(api, (13, 35, 1)), False),    # complex hopping + bond pairing: DMMA rows
+    "readme_3_3_1": (lambda api: cases.readme_swave(api, (3, 3, 1)), True),        # smallest lattice it accepts
+}
+
+# (BDG_PAIR_SEG, BDG_PAIR_P, BDG_PAIR_WARPS): None = planner's choice
+PLANS = [(None, None, None), (5, 7, None), (1, 1, None), (4, 30, 8), (3, 14, 8), (1000, 2, None)]
+
+
+def _set_plan(monkeypatch, plan):
+    for name, value in zip(("BDG_PAIR_SEG", "BDG_PAIR_P", "BDG_PAIR_WARPS"), plan):
+        if value is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, str(value))
+
+
+def _vectors(sysn, kernel, n_cols, steps, scale):
+    sysn.cheb_begin(n_random=n_cols, seed=5, col_offset=3, scale=scale, kernel=kernel)
+    sysn.cheb_steps(steps)
+    out = sysn.cheb_vectors(n_cols, 0), sysn.cheb_vectors(n_cols, 1)
+    fmt = sysn.cheb_format()["kernel"]
+    sysn.cheb_end()
+    return out, fmt
+
+
+@pytest.mark.parametrize("plan", PLANS)
+@pytest.mark.parametrize("tag", sorted(SYSTEMS))
+def test_pair_vectors_are_bit_identical_to_the_single_step_kernel(gpu_api, monkeypatch, tag, plan):
+    build, diag = SYSTEMS[tag]
+    system = build(gpu_api)
+    scale = system.spectral_bound()
+    base = "dict_diag" if diag else "dict"
+    _set_plan(monkeypatch, plan)
+    for n_cols, steps in ((8, 6), (5, 7), (19, 2), (12, 1)):   # odd counts end on a single step; 1 = no pair at all
+        (cur, prev), fmt = _vectors(system._sys, "pair", n_cols, steps, scale)
+        assert fmt == "pair"
+        (want_cur, want_prev), fmt = _vectors(system._sys, base, n_cols, steps, scale)
+        assert fmt == base
+        assert np.array_equal(cur, want_cur), f"T_n differs: max {np.max(np.abs(cur - want_cur)):.3e}"
+        assert np.array_equal(prev, want_prev), f"T_n-1 differs: max {np.max(np.abs(prev - want_prev)):.3e}"
+
+
+@pytest.mark.parametrize("tag", sorted(SYSTEMS))
+def test_pair_moments_match_the_oracle(gpu_api, monkeypatch, tag):
+    build, diag = SYSTEMS[tag]
+    system = build(gpu_api)
+    H = system.matrix("bsr")
+    scale = system.spectral_bound()
+    for plan in PLANS[:3]:
+        _set_plan(monkeypatch, plan)
+        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2)):
+            got = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="pair")
+            want = orc.cheb_moments(H, orc.rademacher(3, H.shape[0], np.arange(n_cols)), n_moments, scale)
+            assert got.shape == want.shape
+            assert rel_err(got, want) <= TOL
+            single = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="dict_diag" if diag else "dict")
+            assert rel_err(got, single) <= 1e-13   # same vectors, dot products summed in another order
+            again = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="pair")
+            assert np.array_equal(got, again)      # fixed-order reduction: bit-reproducible
+    summed = system.chebyshev_moments(48, vectors=8, seed=3, scale=scale, kernel="pair", summed=True)
+    assert rel_err(summed, system.chebyshev_moments(48, vectors=8, seed=3, scale=scale, kernel="pair").sum(axis=1)) <= 1e-13
+
+
+def test_pair_probe_columns_and_ldos(gpu_api):
+    """Unit start vectors (LDOS-type): sparse vectors spread one site per step, so halo handling errors
+    show up as exact zeros / non-zeros in the wrong place."""
+    system = cases.junction(gpu_api, (30, 40, 1))
+    H = system.matrix("bsr")
+    scale = system.spectral_bound()
+    rows = [4 * system.lattice.index((x, y, 0)) + a for (x, y) in ((0, 0), (29, 39), (14, 29), (15, 30)) for a in (0, 3)]
+    got = system.chebyshev_moments(64, rows=rows, scale=scale, kernel="pair")
+    x0 = np.zeros((H.shape[0], len(rows)), dtype=np.complex128)
+    x0[rows, np.arange(len(rows))] = 1.0
+    assert rel_err(got, orc.cheb_moments(H, x0, 64, scale)) <= TOL
+    E = np.linspace(-0.3, 0.3, 9)
+    sites = [(14, 29, 0), (0, 39, 0)]   # 2 sites x 4 components = one 8-column panel
+    assert rel_err(system.ldos_map(sites, E, kernel="pair"), system.ldos_map(sites, E, kernel="dict_diag")) <= 1e-12
+
+
+def test_pair_declines_what_it_cannot_do(gpu_api):
+    scale = 10.0
+    three_d = cases.swave_3d(gpu_api, (6, 5, 4))._sys            # two-dimensional x-planes
+    with pytest.raises(ValueError):
+        three_d.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
+    periodic = cases.random_periodic(gpu_api, (3, 5, 7), seed=11)._sys   # no dictionary, wrap-around bonds
+    with pytest.raises(ValueError):
+        periodic.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
+    flat = cases.readme_swave(gpu_api, (12, 12, 1))
+    with pytest.raises(ValueError):                              # panels of fewer than 8 columns
+        flat._sys.cheb_begin(n_random=4, seed=1, scale=scale, kernel="pair")
+    # wrap-around hopping along y on an otherwise qualifying lattice
+    lattice = flat.lattice
+    with flat as (H, D):
+        for x in range(12):
+            H[(x, 0, 0), (x, 11, 0)] = -1.0 * gpu_api.σ0
+            H[(x, 11, 0), (x, 0, 0)] = -1.0 * gpu_api.σ0
+    with pytest.raises(ValueError):
+        flat._sys.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
+    got = flat.chebyshev_moments(16, vectors=8, seed=2, kernel="auto")   # ... and auto still works on it
+    H2 = flat.matrix("bsr")
+    assert rel_err(got, orc.cheb_moments(H2, orc.rademacher(2, H2.shape[0], np.arange(8)), 16, flat.spectral_bound())) <= TOL
+    assert lattice.size == 144
+
+
+def test_pair_follows_matrix_updates(gpu_api):
+    system = cases.readme_swave(gpu_api, (10, 12, 1))
+    scale = system.spectral_bound() * 1.2
+    before = system.chebyshev_moments(32, vectors=8, seed=2, scale=scale, kernel="pair")
+    with system as (H, D):
+        H[(4, 4, 0), (4, 4, 0)] = 0.7 * gpu_api.σ0 + 0.2 * gpu_api.σ3
+    after = system.chebyshev_moments(32, vectors=8, seed=2, scale=scale, kernel="pair")
+    assert not np.array_equal(before, after)
+    Hm = system.matrix("bsr")
+    assert rel_err(after, orc.cheb_moments(Hm, orc.rademacher(2, Hm.shape[0], np.arange(8)), 32, scale)) <= TOL
+
+
+def test_pair_full_size_junction():
+    """C5 (10^6 sites, 8 columns): vectors after 2 x 3 + 1 steps bit-identical to the single-step kernel,
+    moments to rounding, mu_0 = 4N exactly, bit-reproducible."""
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    c = workloads.CONFIGS["C5"]
+    system = b.Hamiltonian(b.CubicLattice(c["shape"]))
+    assert system.fill(*c["build"](c["shape"])) == 0.0
+    scale = system.spectral_bound()
+    (cur, prev), fmt = _vectors(system._sys, "pair", 8, 7, scale)
+    assert fmt == "pair"
+    (want_cur, want_prev), _ = _vectors(system._sys, "dict_diag", 8, 7, scale)
+    assert np.array_equal(cur, want_cur) and np.array_equal(prev, want_prev)
+    del cur, prev, want_cur, want_prev
+    pair = system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale, kernel="pair")
+    single = system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale, kernel="dict_diag")
+    assert rel_err(pair, single) <= 1e-13
+    assert np.array_equal(pair[0], np.full(8, float(system.shape[0])))
+    assert np.array_equal(pair, system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale, kernel="pair"))
