@@ -81,6 +81,7 @@ struct PairWalk {
     int Lx = 1, M = 1;
     int P = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
+    int l2_ahead = 0;  // planes ahead of the shared-memory loads that are pulled into L2 (0 = off)
 };
 
 // ---- Chebyshev state ----------------------------------------------------------------------
@@ -137,6 +138,7 @@ struct EllDev {
     // lattice whose x-planes are one-dimensional (pair_M sites per plane).
     bool pair_usable = false;
     int pair_M = 0;
+    DevBuf dcode;  // int32 [n_sites][5]: dictionary code per stencil direction (self, x-1, y-1, y+1, x+1), -1 = none
     DevBuf tmp_keys, tmp_rep, tmp_where, tmp_dense;  // hash-table scratch of the dictionary build (kept for rebuilds)
 };
 

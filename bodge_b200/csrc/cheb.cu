@@ -696,7 +696,7 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
         if (st.pair)  // one pass over the codes and indices serves two steps
-            *matrix_bytes_per_step = e.n_sites * e.width * 4 + e.n_unique * 256;
+            *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_ELL)

@@ -540,6 +540,7 @@ void ell_release(bdg_system *sys) {
     dev_free(sys, sys->ell.code);
     dev_free(sys, sys->ell.table);
     dev_free(sys, sys->ell.dtab);
+    dev_free(sys, sys->ell.dcode);
     dev_free(sys, sys->ell.tmp_keys);
     dev_free(sys, sys->ell.tmp_rep);
     dev_free(sys, sys->ell.tmp_where);

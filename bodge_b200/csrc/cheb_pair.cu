@@ -77,28 +77,38 @@ __device__ __forceinline__ void ld_table_pred(double &v, const double *p, unsign
     asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(v) : "l"(p), "r"(take));
 }
 
-// B fragments of a row (cheb_ell.cu: DICT / DIAG): reloaded only when a code differs from the held one.
-template <int CH, bool DIAG>
-__device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[CH], const double *__restrict__ table,
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
+
+constexpr int kDirs = 5;  // direction-ordered row: self, x-1, y-1, y+1, x+1 (= ascending block column)
+
+// B fragments of a row (cheb_ell.cu: DICT / DIAG), held in registers from row to row and reloaded only
+// when a code differs from the held one.  Lanes 0..4 carry the row's codes; code < 0 = no block.
+template <bool DIAG>
+__device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[kDirs], const double *__restrict__ table,
                                                const double *__restrict__ dtab, int lane) {
-    const unsigned changed = __ballot_sync(kFull, jv != jheld) >> 8;
+    const unsigned changed = __ballot_sync(kFull, jv != jheld);
     if (changed) {
         jheld = jv;
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int code = __shfl_sync(kFull, jv, 8 + u);
-            const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : table + (size_t)code * 32 + lane;
-            ld_table_pred(keep[u], entry, changed >> u & 1u);
+        for (int u = 0; u < kDirs; ++u) {
+            const int code = __shfl_sync(kFull, jv, u);
+            const unsigned take = changed >> u & 1u;
+            const size_t c = (size_t)max(code, 0);
+            const double *entry = (DIAG && u > 0) ? dtab + c * 4 + (lane & 3) : table + c * 32 + lane;
+            ld_table_pred(keep[u], entry, take && code >= 0);
+            if (take && code < 0) keep[u] = 0.0;
         }
     }
 }
 
 // y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell.
-template <int CH, bool DIAG>
-__device__ __forceinline__ void row_product(const double2 (&xv)[CH], const double (&bop)[CH], double &yr, double &yi) {
+template <bool DIAG>
+__device__ __forceinline__ void row_product(const double2 (&xv)[kDirs], const double (&bop)[kDirs], double &yr, double &yi) {
     double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
 #pragma unroll
-    for (int u = 0; u < (DIAG ? 1 : CH); ++u) {
+    for (int u = 0; u < (DIAG ? 1 : kDirs); ++u) {
         dmma_8x8x4(a10, a11, xv[u].x, bop[u]);
         dmma_8x8x4(a20, a21, xv[u].y, bop[u]);
     }
@@ -106,7 +116,7 @@ __device__ __forceinline__ void row_product(const double2 (&xv)[CH], const doubl
     yi = a11 + a20;
     if (DIAG) {
 #pragma unroll
-        for (int u = 1; u < CH; ++u) {
+        for (int u = 1; u < kDirs; ++u) {
             yr = fma(bop[u], xv[u].x, yr);
             yi = fma(bop[u], xv[u].y, yi);
         }
@@ -115,14 +125,19 @@ __device__ __forceinline__ void row_product(const double2 (&xv)[CH], const doubl
 
 // NW warps per CTA, S sites per warp and plane: W = NW * S sites per plane in sub-step [A]
 // (P <= W - 2 of them owned).  Dynamic shared memory: kRing x ((W + 2) + W + W) records + barriers.
-template <int CH, bool DIAG, int NW, int S>
+//
+// The matrix arrives as `dcode[row][5]`: the dictionary code of the row's block in each stencil
+// direction (self, x-1, y-1, y+1, x+1; -1 = none), so the records a row needs sit at fixed offsets from
+// its own in the rings -- no per-row index arithmetic.  A direction without a lattice site (boundary)
+// reads the row's own record against a zero fragment.  Warps whose site does not exist (ragged last
+// patch) compute on whatever the rings hold and store nothing: the row body has no branches.
+template <bool DIAG, int NW, int S>
 __global__ void __launch_bounds__(NW * 32, 16 / NW)
-cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode, const double *__restrict__ table,
-               const double *__restrict__ dtab, const double2 *__restrict__ xa /* T_{n-1} */,
-               const double2 *__restrict__ xb /* T_n */, double2 *__restrict__ xc /* T_{n+1} */,
-               double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels, double alpha, double beta,
-               double *__restrict__ partials, unsigned *__restrict__ tickets, double *__restrict__ dots_step,
-               const PairWalk wk) {
+cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
+               const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
+               double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
+               double alpha, double beta, double *__restrict__ partials, unsigned *__restrict__ tickets,
+               double *__restrict__ dots_step, const PairWalk wk) {
     constexpr int W = NW * S;
     constexpr uint32_t PLANE_N = (W + 2) * kRecBytes, PLANE_W = W * kRecBytes;
     extern __shared__ __align__(128) unsigned char pair_smem[];
@@ -136,9 +151,7 @@ cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ cco
     const size_t pbase = (size_t)panel * n_sites * 32;
     const double2 *ta = xa + pbase, *tb = xb + pbase;
     double2 *tc = xc + pbase, *td = xd + pbase;
-    // Per-row index fetch: lanes 0..CH-1 read the slot's block column, lanes 8..8+CH-1 its code.
-    const int32_t *islot = lane >= 8 ? ccode - 8 : cidx;
-    const bool ilane = (lane & 7) < CH && lane < 16;
+    const bool clane = lane < kDirs;
     const uint32_t lane16 = (uint32_t)lane * 16u;
 
     if (threadIdx.x == 0) {
@@ -150,13 +163,13 @@ cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ cco
     uint32_t phases = 0;  // bit r = parity of the next completion of ring slot r
 
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    double keep[S][CH];
+    double keep[S][kDirs];
     int jheld[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        jheld[s] = -1;
+        jheld[s] = -2;
 #pragma unroll
-        for (int u = 0; u < CH; ++u) keep[s][u] = 0.0;
+        for (int u = 0; u < kDirs; ++u) keep[s][u] = 0.0;
     }
 
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
@@ -182,6 +195,12 @@ cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ cco
                     if (with_prev)
                         bulk_g2s(sTp + r * PLANE_W + (uint32_t)(plo - (y0 - 1)) * kRecBytes,
                                  ta + ((size_t)q * wk.M + plo) * 32, pbytes, sBar + 8 * r);
+                    // ... and pull the planes a few iterations further on into L2
+                    const int far = q + wk.l2_ahead;
+                    if (wk.l2_ahead > 0 && far < thi) {
+                        bulk_prefetch_l2(tb + ((size_t)far * wk.M + nlo) * 32, nbytes);
+                        if (far < xhi) bulk_prefetch_l2(ta + ((size_t)far * wk.M + plo) * 32, (uint32_t)(phi - plo) * kRecBytes);
+                    }
                 }
             }
         };
@@ -190,17 +209,24 @@ cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ cco
         issue_upto(xlo + 2);
 
         int yy[S], jvA[S], jvB[S];
-        bool exists[S], owned[S];
+        bool owned[S];
+        uint32_t aN[S], aP[S], a1[S], off_ym[S], off_yp[S];
         double2 tnA[S], tnB[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int l = warp + NW * s;
             yy[s] = y0 - 1 + l;
-            exists[s] = l < wk.P + 2 && yy[s] >= 0 && yy[s] < wk.M;
-            owned[s] = exists[s] && l >= 1 && l <= wk.P;
-            jvA[s] = jvB[s] = 0;
+            const bool exists = l < wk.P + 2 && yy[s] >= 0 && yy[s] < wk.M;
+            owned[s] = exists && l >= 1 && l <= wk.P;
+            if (!exists) yy[s] = min(max(y0, 0), wk.M - 1);  // any valid row: its codes are read, its result dropped
+            off_ym[s] = exists && yy[s] > 0 ? (uint32_t)-kRecBytes : 0u;
+            off_yp[s] = exists && yy[s] < wk.M - 1 ? (uint32_t)kRecBytes : 0u;
+            aN[s] = sTn + (uint32_t)(l + 1) * kRecBytes + lane16;
+            aP[s] = sTp + (uint32_t)l * kRecBytes + lane16;
+            a1[s] = sT1 + (uint32_t)l * kRecBytes + lane16;
+            jvA[s] = jvB[s] = -1;
             tnA[s] = tnB[s] = make_double2(0.0, 0.0);
-            if (exists[s] && ilane) jvA[s] = __ldg(islot + ((size_t)xlo * wk.M + yy[s]) * CH + lane);
+            if (clane) jvA[s] = __ldg(dcode + ((size_t)xlo * wk.M + yy[s]) * kDirs + lane);
         }
 
         for (int x = xlo; x <= x1; ++x) {
@@ -216,61 +242,67 @@ cheb_pair_step(const int32_t *__restrict__ cidx, const int32_t *__restrict__ cco
             int jnext[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                jnext[s] = 0;
-                if (do_a && x + 1 < xhi && exists[s] && ilane) jnext[s] = __ldg(islot + ((size_t)(x + 1) * wk.M + yy[s]) * CH + lane);
+                jnext[s] = -1;
+                if (do_a && x + 1 < xhi && clane) jnext[s] = __ldg(dcode + ((size_t)(x + 1) * wk.M + yy[s]) * kDirs + lane);
             }
             if (do_a) {
                 const bool store = x >= x0 && x < x1;
-                const uint32_t slot = (uint32_t)(x & (kRing - 1));
+                const uint32_t r0 = (uint32_t)(x & (kRing - 1));
+                const uint32_t n0 = r0 * PLANE_N, p0 = r0 * PLANE_W;
+                const uint32_t nm = x > 0 ? (uint32_t)((x - 1) & (kRing - 1)) * PLANE_N : n0;
+                const uint32_t np = x + 1 < wk.Lx ? (uint32_t)((x + 1) & (kRing - 1)) * PLANE_N : n0;
+                double2 xv[S][kDirs], pv[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    if (!exists[s]) continue;  // warp-uniform
-                    const int l = warp + NW * s;
-                    const int row = x * wk.M + yy[s];
-                    hold_fragments<CH, DIAG>(jvA[s], jheld[s], keep[s], table, dtab, lane);
-                    // lane u < CH: where the record of slot u's block column sits in the T_n ring
-                    const int dj = jvA[s] - row;
-                    const int dxp = (dj >= wk.M) - (dj <= -wk.M);
-                    const int dl = dj - dxp * wk.M;
-                    const uint32_t mine = (uint32_t)((x + dxp) & (kRing - 1)) * PLANE_N + (uint32_t)(l + 1 + dl) * kRecBytes;
-                    double2 xv[CH];
+                    hold_fragments<DIAG>(jvA[s], jheld[s], keep[s], table, dtab, lane);
+                    xv[s][0] = lds_rec(aN[s] + n0);
+                    xv[s][1] = lds_rec(aN[s] + nm);
+                    xv[s][2] = lds_rec(aN[s] + n0 + off_ym[s]);
+                    xv[s][3] = lds_rec(aN[s] + n0 + off_yp[s]);
+                    xv[s][4] = lds_rec(aN[s] + np);
+                    pv[s] = lds_rec(aP[s] + p0);
+                }
 #pragma unroll
-                    for (int u = 0; u < CH; ++u) xv[u] = lds_rec(sTn + __shfl_sync(kFull, mine, u) + lane16);
-                    const double2 pv = lds_rec(sTp + slot * PLANE_W + (uint32_t)l * kRecBytes + lane16);
+                for (int s = 0; s < S; ++s) {
                     double yr, yi;
-                    row_product<CH, DIAG>(xv, keep[s], yr, yi);
-                    const double2 out = make_double2(alpha * yr - beta * pv.x, alpha * yi - beta * pv.y);
-                    sts_rec(sT1 + slot * PLANE_W + (uint32_t)l * kRecBytes + lane16, out);
-                    tnA[s] = xv[0];  // slot 0 is the row's own record
+                    row_product<DIAG>(xv[s], keep[s], yr, yi);
+                    const double2 out = make_double2(alpha * yr - beta * pv[s].x, alpha * yi - beta * pv[s].y);
+                    sts_rec(a1[s] + p0, out);
+                    tnA[s] = xv[s][0];
                     if (store && owned[s]) {
-                        tc[(size_t)row * 32 + lane] = out;
-                        d0 += xv[0].x * xv[0].x + xv[0].y * xv[0].y;
-                        d1 += out.x * xv[0].x + out.y * xv[0].y;
+                        tc[((size_t)x * wk.M + yy[s]) * 32 + lane] = out;
+                        d0 += xv[s][0].x * xv[s][0].x + xv[s][0].y * xv[s][0].y;
+                        d1 += out.x * xv[s][0].x + out.y * xv[s][0].y;
                     }
                 }
             }
             __syncthreads();  // T_{n+1}(x) complete in the ring
             if (x - 1 >= x0) {
                 const int xb1 = x - 1;
+                const uint32_t q0 = (uint32_t)(xb1 & (kRing - 1)) * PLANE_W;
+                const uint32_t qm = xb1 > 0 ? (uint32_t)((xb1 - 1) & (kRing - 1)) * PLANE_W : q0;
+                const uint32_t qp = xb1 + 1 < wk.Lx ? (uint32_t)((xb1 + 1) & (kRing - 1)) * PLANE_W : q0;
+                double2 xv[S][kDirs];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    if (!owned[s]) continue;  // warp-uniform
-                    const int l = warp + NW * s;
-                    const int row = xb1 * wk.M + yy[s];
-                    hold_fragments<CH, DIAG>(jvB[s], jheld[s], keep[s], table, dtab, lane);
-                    const int dj = jvB[s] - row;
-                    const int dxp = (dj >= wk.M) - (dj <= -wk.M);
-                    const int dl = dj - dxp * wk.M;
-                    const uint32_t mine = (uint32_t)((xb1 + dxp) & (kRing - 1)) * PLANE_W + (uint32_t)(l + dl) * kRecBytes;
-                    double2 xv[CH];
+                    hold_fragments<DIAG>(jvB[s], jheld[s], keep[s], table, dtab, lane);
+                    xv[s][0] = lds_rec(a1[s] + q0);
+                    xv[s][1] = lds_rec(a1[s] + qm);
+                    // (halo rows compute a dropped result here: keep their reads inside the ring)
+                    xv[s][2] = lds_rec(a1[s] + q0 + (owned[s] ? off_ym[s] : 0u));
+                    xv[s][3] = lds_rec(a1[s] + q0 + (owned[s] ? off_yp[s] : 0u));
+                    xv[s][4] = lds_rec(a1[s] + qp);
+                }
 #pragma unroll
-                    for (int u = 0; u < CH; ++u) xv[u] = lds_rec(sT1 + __shfl_sync(kFull, mine, u) + lane16);
+                for (int s = 0; s < S; ++s) {
                     double yr, yi;
-                    row_product<CH, DIAG>(xv, keep[s], yr, yi);
+                    row_product<DIAG>(xv[s], keep[s], yr, yi);
                     const double2 out = make_double2(alpha * yr - beta * tnB[s].x, alpha * yi - beta * tnB[s].y);
-                    td[(size_t)row * 32 + lane] = out;
-                    d2 += xv[0].x * xv[0].x + xv[0].y * xv[0].y;
-                    d3 += out.x * xv[0].x + out.y * xv[0].y;
+                    if (owned[s]) {
+                        td[((size_t)xb1 * wk.M + yy[s]) * 32 + lane] = out;
+                        d2 += xv[s][0].x * xv[s][0].x + xv[s][0].y * xv[s][0].y;
+                        d3 += out.x * xv[s][0].x + out.y * xv[s][0].y;
+                    }
                 }
             }
 #pragma unroll
@@ -342,23 +374,31 @@ pair_check(int64_t n_slots, int width, int M, const int32_t *__restrict__ cidx, 
     if (!ok) *bad = 1;
 }
 
-using PairKernel = void (*)(const int32_t *, const int32_t *, const double *, const double *, const double2 *,
-                            const double2 *, double2 *, double2 *, int, int, double, double, double *, unsigned *,
-                            double *, const PairWalk);
+// dcode[row][dir] = dictionary code of the row's block towards (self, x-1, y-1, y+1, x+1), -1 = none.
+// Slot 0 of the fixed-width copy is the diagonal block; padding slots point at the row itself.
+__global__ void __launch_bounds__(256)
+pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode,
+           int32_t *__restrict__ dcode) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_sites) return;
+    int out[kDirs] = {-1, -1, -1, -1, -1};
+    for (int u = 0; u < width; ++u) {
+        const int d = cidx[(size_t)row * width + u] - row, c = ccode[(size_t)row * width + u];
+        if (u == 0) out[0] = c;
+        else if (d == -M) out[1] = c;
+        else if (d == -1) out[2] = c;
+        else if (d == 1) out[3] = c;
+        else if (d == M) out[4] = c;
+    }
+#pragma unroll
+    for (int k = 0; k < kDirs; ++k) dcode[(size_t)row * kDirs + k] = out[k];
+}
 
-template <int NW, int S> PairKernel pick_pair_shape(bool diag, int width) {
-    if (diag) {
-        switch (width) {
-            case 3: return cheb_pair_step<3, true, NW, S>;
-            case 4: return cheb_pair_step<4, true, NW, S>;
-            default: return cheb_pair_step<5, true, NW, S>;
-        }
-    }
-    switch (width) {
-        case 3: return cheb_pair_step<3, false, NW, S>;
-        case 4: return cheb_pair_step<4, false, NW, S>;
-        default: return cheb_pair_step<5, false, NW, S>;
-    }
+using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
+                            double2 *, int, int, double, double, double *, unsigned *, double *, const PairWalk);
+
+template <int NW, int S> PairKernel pick_pair_shape(bool diag) {
+    return diag ? cheb_pair_step<true, NW, S> : cheb_pair_step<false, NW, S>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -372,14 +412,14 @@ struct PairShape {
     size_t smem;
 };
 
-PairShape pair_shape(bool diag, int width) {
+PairShape pair_shape(bool diag) {
     PairShape s;
-    if (env_int("BDG_PAIR_WARPS", 16) <= 8) {
+    if (env_int("BDG_PAIR_WARPS", 8) <= 8) {  // two CTAs per SM: one computes while the other waits at its barrier
         s.warps = 8, s.sites = 2;
-        s.kernel = pick_pair_shape<8, 2>(diag, width);
+        s.kernel = pick_pair_shape<8, 2>(diag);
     } else {
         s.warps = 16, s.sites = 2;
-        s.kernel = pick_pair_shape<16, 2>(diag, width);
+        s.kernel = pick_pair_shape<16, 2>(diag);
     }
     const int W = s.warps * s.sites;
     s.smem = (size_t)kRing * ((W + 2) + 2 * W) * kRecBytes + 64;
@@ -410,6 +450,12 @@ int pair_probe(bdg_system *sys) {
     BDG_CUDA(cudaStreamSynchronize(sys->stream));
     e.pair_usable = host == 0;
     e.pair_M = M;
+    if (e.pair_usable) {
+        BDG_TRY(dev_alloc(sys, e.dcode, (size_t)e.n_sites * kDirs * sizeof(int32_t)));
+        pair_codes<<<(unsigned)ceil_div(e.n_sites, 256), 256, 0, sys->stream>>>((int)e.n_sites, e.width, M, e.idx.as<int32_t>(),
+                                                                              e.code.as<int32_t>(), e.dcode.as<int32_t>());
+        BDG_CUDA(cudaGetLastError());
+    }
     return BDG_OK;
 }
 
@@ -417,7 +463,7 @@ int pair_probe(bdg_system *sys) {
 int pair_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, e.width);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG);
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
@@ -449,6 +495,7 @@ int pair_configure(bdg_system *sys) {
         }
         if (forced > 0) break;
     }
+    w.l2_ahead = std::max(0, env_int("BDG_PAIR_L2_AHEAD", 0));
     st.pair_grid_x = (int)std::min<int64_t>(slots, w.n_items);
     return BDG_OK;
 }
@@ -458,11 +505,10 @@ int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
     const bool diag = st.kernel == BDG_KERNEL_DICT_DIAG;
-    const PairShape shape = pair_shape(diag, e.width);
+    const PairShape shape = pair_shape(diag);
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
-        e.idx.as<int32_t>(), e.code.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(),
-        static_cast<const double2 *>(x_prev), static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1),
+        e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev), static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1),
         static_cast<double2 *>(x_next2), (int)e.n_sites, st.n_panels, 2.0 / st.scale, 1.0, st.partials.as<double>(),
         st.tickets.as<unsigned>(), dots_step, st.pair_walk);
     BDG_CUDA(cudaGetLastError());
