@@ -31,7 +31,10 @@
 
 namespace {
 
-constexpr bool kAutoPairDefault = false;  // flipped once the pair kernel is measured ahead (profiles/)
+// AUTO runs two steps per pass wherever the DFMA variant of the pair kernel applies: 1.33x the single-step
+// dictionary kernel at C5 (profiles/r01/s4_pair_v2.log).  The DMMA variant (complex hopping / pairing on the
+// bonds, C3) is FP64-pipe-bound and slower than its single-step kernel, so it stays opt-in.
+constexpr bool kAutoPairDefault = true;
 
 
 // ---- the fused step: FP64 warp-MMA formulation --------------------------------------------------
@@ -489,7 +492,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
         BDG_REQUIRE(kernel != BDG_KERNEL_PAIR || pair_ok,
                     "the two-steps-per-pass kernel needs >= 5 columns and a block dictionary on a lattice with "
                     "one-dimensional x-planes and an open nearest-neighbour stencil");
-        pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && pair_ok && auto_pair_enabled());
+        pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && pair_ok && sys->ell.diag_usable && auto_pair_enabled());
         if (kernel == BDG_KERNEL_PAIR) kernel = BDG_KERNEL_AUTO;
         BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
                     "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");

@@ -247,7 +247,7 @@ class Hamiltonian:
         rank, world, group = distributed.resolve(group)
         lo, hi = distributed.shard_range(n_total, rank, world)
         n_local = hi - lo
-        if batch is None:  # two vector sets of 64*N*k bytes each; keep them under ~16 GB
+        if batch is None:  # two vector sets of 64*N*k bytes each (four with the pair kernel); keep two under ~16 GB
             batch = max(8, int(8e9 // (64 * self.lattice.size)) // 8 * 8)
         steps = (moments + 1) // 2 - 1
         parts = []

@@ -126,6 +126,28 @@ def test_pair_declines_what_it_cannot_do(gpu_api):
     assert lattice.size == 144
 
 
+def test_auto_prefers_pair_where_it_is_faster(gpu_api, monkeypatch):
+    """kernel="auto": two steps per pass when the hopping blocks are real-diagonal (DFMA rows) and a panel
+    has 8 columns; single-step kernels otherwise; BDG_AUTO_PAIR=0 switches the preference off."""
+    scale = 10.0
+    flat = cases.readme_swave(gpu_api, (12, 12, 1))._sys
+    for n_cols, want in ((8, "pair"), (19, "pair"), (5, "pair"), (4, "dict_diag"), (1, "dict_diag")):
+        flat.cheb_begin(n_random=n_cols, seed=1, scale=scale, kernel="auto")
+        assert flat.cheb_format()["kernel"] == want
+    monkeypatch.setenv("BDG_AUTO_PAIR", "0")
+    flat.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
+    assert flat.cheb_format()["kernel"] == "dict_diag"
+    monkeypatch.delenv("BDG_AUTO_PAIR")
+    dwave = cases.dwave_rashba(gpu_api, (9, 8, 1))._sys          # complex hopping blocks: DMMA rows
+    dwave.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
+    assert dwave.cheb_format()["kernel"] == "dict"
+    cube = cases.swave_3d(gpu_api, (6, 5, 4))._sys
+    cube.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
+    assert cube.cheb_format()["kernel"] == "dict_diag"
+    for sysn in (flat, dwave, cube):
+        sysn.cheb_end()
+
+
 def test_pair_follows_matrix_updates(gpu_api):
     system = cases.readme_swave(gpu_api, (10, 12, 1))
     scale = system.spectral_bound() * 1.2
