@@ -83,94 +83,123 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes
 
 constexpr int kDirs = 5;  // direction-ordered row: self, x-1, y-1, y+1, x+1 (= ascending block column)
 
-// B fragments of a row (cheb_ell.cu: DICT / DIAG), held in registers from row to row and reloaded only
-// when a code differs from the held one.  Lanes 0..4 carry the row's codes; code < 0 = no block.
-template <bool DIAG>
-__device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[kDirs], const double *__restrict__ table,
+// Keep a value in its register: the compiler otherwise re-derives loop invariants (shared-memory
+// base, lane offsets) inside the row loop, which is instruction-issue-bound.
+__device__ __forceinline__ void pin(uint32_t &v) { asm volatile("" : "+r"(v)); }
+
+// B fragments of the S rows a warp handles (cheb_ell.cu: DICT / DIAG), held in registers from plane to
+// plane and reloaded only when a code differs from the held one.  Lane s * 5 + u carries the code of
+// row s, direction u; code < 0 = no block.
+template <bool DIAG, int S>
+__device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[S][kDirs], const double *__restrict__ table,
                                                const double *__restrict__ dtab, int lane) {
     const unsigned changed = __ballot_sync(kFull, jv != jheld);
     if (changed) {
         jheld = jv;
 #pragma unroll
-        for (int u = 0; u < kDirs; ++u) {
-            const int code = __shfl_sync(kFull, jv, u);
-            const unsigned take = changed >> u & 1u;
-            const size_t c = (size_t)max(code, 0);
-            const double *entry = (DIAG && u > 0) ? dtab + c * 4 + (lane & 3) : table + c * 32 + lane;
-            ld_table_pred(keep[u], entry, take && code >= 0);
-            if (take && code < 0) keep[u] = 0.0;
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int u = 0; u < kDirs; ++u) {
+                const int code = __shfl_sync(kFull, jv, s * kDirs + u);
+                const unsigned take = changed >> (s * kDirs + u) & 1u;
+                const size_t c = (size_t)max(code, 0);
+                const double *entry = (DIAG && u > 0) ? dtab + c * 4 + (lane & 3) : table + c * 32 + lane;
+                ld_table_pred(keep[s][u], entry, take && code >= 0);
+                if (take && code < 0) keep[s][u] = 0.0;
+            }
         }
     }
 }
 
-// y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell.
+// y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell
+// (directions: self, x-1, y-1, y+1, x+1 = ascending block column).
 template <bool DIAG>
-__device__ __forceinline__ void row_product(const double2 (&xv)[kDirs], const double (&bop)[kDirs], double &yr, double &yi) {
+__device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1, const double2 &x2, const double2 &x3,
+                                            const double2 &x4, const double (&bop)[kDirs], double &yr, double &yi) {
     double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
-#pragma unroll
-    for (int u = 0; u < (DIAG ? 1 : kDirs); ++u) {
-        dmma_8x8x4(a10, a11, xv[u].x, bop[u]);
-        dmma_8x8x4(a20, a21, xv[u].y, bop[u]);
+    dmma_8x8x4(a10, a11, x0.x, bop[0]);
+    dmma_8x8x4(a20, a21, x0.y, bop[0]);
+    if (!DIAG) {
+        dmma_8x8x4(a10, a11, x1.x, bop[1]);
+        dmma_8x8x4(a20, a21, x1.y, bop[1]);
+        dmma_8x8x4(a10, a11, x2.x, bop[2]);
+        dmma_8x8x4(a20, a21, x2.y, bop[2]);
+        dmma_8x8x4(a10, a11, x3.x, bop[3]);
+        dmma_8x8x4(a20, a21, x3.y, bop[3]);
+        dmma_8x8x4(a10, a11, x4.x, bop[4]);
+        dmma_8x8x4(a20, a21, x4.y, bop[4]);
     }
     yr = a10 - a21;
     yi = a11 + a20;
     if (DIAG) {
-#pragma unroll
-        for (int u = 1; u < kDirs; ++u) {
-            yr = fma(bop[u], xv[u].x, yr);
-            yi = fma(bop[u], xv[u].y, yi);
-        }
+        yr = fma(bop[1], x1.x, yr);
+        yi = fma(bop[1], x1.y, yi);
+        yr = fma(bop[2], x2.x, yr);
+        yi = fma(bop[2], x2.y, yi);
+        yr = fma(bop[3], x3.x, yr);
+        yi = fma(bop[3], x3.y, yi);
+        yr = fma(bop[4], x4.x, yr);
+        yi = fma(bop[4], x4.y, yi);
     }
 }
 
-// NW warps per CTA, S sites per warp and plane: W = NW * S sites per plane in sub-step [A]
-// (P <= W - 2 of them owned).  Dynamic shared memory: kRing x ((W + 2) + W + W) records + barriers.
+// NW warps per CTA, two ADJACENT sites per warp and plane: W = 2 NW sites per plane in sub-step [A]
+// (P <= W - 2 of them owned).  Dynamic shared memory: kRing x ((W + 2) + W + W) records + a guard
+// record + barriers.
 //
 // The matrix arrives as `dcode[row][5]`: the dictionary code of the row's block in each stencil
 // direction (self, x-1, y-1, y+1, x+1; -1 = none), so the records a row needs sit at fixed offsets from
-// its own in the rings -- no per-row index arithmetic.  A direction without a lattice site (boundary)
-// reads the row's own record against a zero fragment.  Warps whose site does not exist (ragged last
-// patch) compute on whatever the rings hold and store nothing: the row body has no branches.
-template <bool DIAG, int NW, int S>
+// its own in the rings -- no per-row index arithmetic, and the two sites of a warp share their
+// in-plane neighbours (4 loads for 6 operands).  A direction without a lattice site (boundary) is read
+// all the same and meets a zero fragment: the rings are cleared once, so whatever sits there is an
+// earlier, finite, vector value.  Warps whose site does not exist (ragged last patch) compute on
+// whatever the rings hold and store nothing: the row body has no branches.
+template <bool DIAG, int NW>
 __global__ void __launch_bounds__(NW * 32, 16 / NW)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
                double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
                double alpha, double beta, double *__restrict__ partials, unsigned *__restrict__ tickets,
                double *__restrict__ dots_step, const PairWalk wk) {
-    constexpr int W = NW * S;
-    constexpr uint32_t PLANE_N = (W + 2) * kRecBytes, PLANE_W = W * kRecBytes;
+    constexpr int S = 2, W = NW * S, R = kRecBytes;
+    constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
     extern __shared__ __align__(128) unsigned char pair_smem[];
     const uint32_t sTn = smem_u32(pair_smem);         // T_n planes, local site l2 = y - (y0 - 2)
     const uint32_t sTp = sTn + kRing * PLANE_N;       // T_{n-1} planes, local site l = y - (y0 - 1)
     const uint32_t sT1 = sTp + kRing * PLANE_W;       // T_{n+1} planes (computed here), local site l
-    const uint32_t sBar = sT1 + kRing * PLANE_W;      // one mbarrier per ring slot
+    const uint32_t sBar = sT1 + kRing * PLANE_W + R;  // guard record (halo rows of [B] read one past the ring), then one mbarrier per slot
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int panel = blockIdx.y;
     const size_t pbase = (size_t)panel * n_sites * 32;
     const double2 *ta = xa + pbase, *tb = xb + pbase;
     double2 *tc = xc + pbase, *td = xd + pbase;
-    const bool clane = lane < kDirs;
-    const uint32_t lane16 = (uint32_t)lane * 16u;
+    const int l0 = S * warp;  // this warp's sites: l0, l0 + 1
+    // own-record addresses of site l0 in slot 0 of each ring (+ lane's 16 bytes)
+    uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
+    uint32_t aP = sTp + (uint32_t)l0 * R + (uint32_t)lane * 16u;
+    uint32_t a1 = sT1 + (uint32_t)l0 * R + (uint32_t)lane * 16u;
+    pin(aN), pin(aP), pin(a1);
 
+    for (uint32_t o = threadIdx.x * 16u; o < kRing * (PLANE_N + 2 * PLANE_W) + R; o += NW * 32 * 16u)
+        sts_rec(sTn + o, make_double2(0.0, 0.0));
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int r = 0; r < kRing; ++r) mbar_init(sBar + 8 * r, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
     __syncthreads();
     uint32_t phases = 0;  // bit r = parity of the next completion of ring slot r
 
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
     double keep[S][kDirs];
-    int jheld[S];
+    int jheld = -2;
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        jheld[s] = -2;
+    for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int u = 0; u < kDirs; ++u) keep[s][u] = 0.0;
-    }
+    const int code_last = n_sites * kDirs - 1;
 
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
         const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
@@ -179,138 +208,126 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         const int tlo = max(0, xlo - 1), thi = min(wk.Lx, xhi + 1);  // T_n planes they read
         const int nlo = max(0, y0 - 2), nhi = min(wk.M, y0 + wk.P + 2);  // in-plane run of T_n
         const int plo = max(0, y0 - 1), phi = min(wk.M, y0 + wk.P + 1);  // ... of T_{n-1}
-        int issued = tlo, waited = tlo;
 
         // Plane q -> ring slot q % kRing: T_n always, T_{n-1} when [A] runs on it; one barrier phase.
-        auto issue_upto = [&](int last) {
-            for (; issued <= last && issued < thi; ++issued) {
-                if (threadIdx.x == 0) {
-                    const int q = issued, r = q & (kRing - 1);
-                    const bool with_prev = q >= xlo && q < xhi;
-                    const uint32_t nbytes = (uint32_t)(nhi - nlo) * kRecBytes;
-                    const uint32_t pbytes = with_prev ? (uint32_t)(phi - plo) * kRecBytes : 0u;
-                    mbar_expect_tx(sBar + 8 * r, nbytes + pbytes);
-                    bulk_g2s(sTn + r * PLANE_N + (uint32_t)(nlo - (y0 - 2)) * kRecBytes, tb + ((size_t)q * wk.M + nlo) * 32,
-                             nbytes, sBar + 8 * r);
-                    if (with_prev)
-                        bulk_g2s(sTp + r * PLANE_W + (uint32_t)(plo - (y0 - 1)) * kRecBytes,
-                                 ta + ((size_t)q * wk.M + plo) * 32, pbytes, sBar + 8 * r);
-                    // ... and pull the planes a few iterations further on into L2
-                    const int far = q + wk.l2_ahead;
-                    if (wk.l2_ahead > 0 && far < thi) {
-                        bulk_prefetch_l2(tb + ((size_t)far * wk.M + nlo) * 32, nbytes);
-                        if (far < xhi) bulk_prefetch_l2(ta + ((size_t)far * wk.M + plo) * 32, (uint32_t)(phi - plo) * kRecBytes);
-                    }
+        auto issue = [&](int q) {
+            if (threadIdx.x == 0 && q < thi) {
+                const int r = q & (kRing - 1);
+                const bool with_prev = q >= xlo && q < xhi;
+                const uint32_t nbytes = (uint32_t)(nhi - nlo) * R;
+                const uint32_t pbytes = with_prev ? (uint32_t)(phi - plo) * R : 0u;
+                mbar_expect_tx(sBar + 8 * r, nbytes + pbytes);
+                bulk_g2s(sTn + r * PLANE_N + (uint32_t)(nlo - (y0 - 2)) * R, tb + ((size_t)q * wk.M + nlo) * 32, nbytes,
+                         sBar + 8 * r);
+                if (with_prev)
+                    bulk_g2s(sTp + r * PLANE_W + (uint32_t)(plo - (y0 - 1)) * R, ta + ((size_t)q * wk.M + plo) * 32, pbytes,
+                             sBar + 8 * r);
+                // ... and pull the planes a few iterations further on into L2
+                const int far = q + wk.l2_ahead;
+                if (wk.l2_ahead > 0 && far < thi) {
+                    bulk_prefetch_l2(tb + ((size_t)far * wk.M + nlo) * 32, nbytes);
+                    if (far < xhi) bulk_prefetch_l2(ta + ((size_t)far * wk.M + plo) * 32, (uint32_t)(phi - plo) * R);
                 }
+            }
+        };
+        auto wait = [&](int q) {
+            if (q < thi) {
+                const int r = q & (kRing - 1);
+                mbar_wait(sBar + 8 * r, (phases >> r) & 1u);
+                phases ^= 1u << r;
             }
         };
 
         __syncthreads();  // every warp is done with the previous item's planes
-        issue_upto(xlo + 2);
+        for (int q = tlo; q <= xlo + 2; ++q) issue(q);
+        for (int q = tlo; q <= xlo; ++q) wait(q);
 
-        int yy[S], jvA[S], jvB[S];
+        // Site l0 + s of this warp: y = y0 - 1 + l0 + s.  Owned = inside the patch and the lattice.
+        const int ya = y0 - 1 + l0;
         bool owned[S];
-        uint32_t aN[S], aP[S], a1[S], off_ym[S], off_yp[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) owned[s] = l0 + s >= 1 && l0 + s <= wk.P && ya + s < wk.M;
+        // lanes 0..9: the codes of the warp's two rows are ten consecutive ints of dcode
+        int cidx = (xlo * wk.M + ya) * kDirs + lane;
+        const int cstep = wk.M * kDirs;
+        int jvA = -1, jvB = -1;
+        if (lane < S * kDirs) jvA = __ldg(dcode + min(max(cidx, 0), code_last));
+        size_t gout = ((size_t)xlo * wk.M + ya) * 32 + lane;  // T_{n+1}(x, ya); the second row 32 elements on
+        const size_t gstep = (size_t)wk.M * 32;
         double2 tnA[S], tnB[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int l = warp + NW * s;
-            yy[s] = y0 - 1 + l;
-            const bool exists = l < wk.P + 2 && yy[s] >= 0 && yy[s] < wk.M;
-            owned[s] = exists && l >= 1 && l <= wk.P;
-            if (!exists) yy[s] = min(max(y0, 0), wk.M - 1);  // any valid row: its codes are read, its result dropped
-            off_ym[s] = exists && yy[s] > 0 ? (uint32_t)-kRecBytes : 0u;
-            off_yp[s] = exists && yy[s] < wk.M - 1 ? (uint32_t)kRecBytes : 0u;
-            aN[s] = sTn + (uint32_t)(l + 1) * kRecBytes + lane16;
-            aP[s] = sTp + (uint32_t)l * kRecBytes + lane16;
-            a1[s] = sT1 + (uint32_t)l * kRecBytes + lane16;
-            jvA[s] = jvB[s] = -1;
-            tnA[s] = tnB[s] = make_double2(0.0, 0.0);
-            if (clane) jvA[s] = __ldg(dcode + ((size_t)xlo * wk.M + yy[s]) * kDirs + lane);
-        }
+        for (int s = 0; s < S; ++s) tnA[s] = tnB[s] = make_double2(0.0, 0.0);
 
-        for (int x = xlo; x <= x1; ++x) {
+        for (int x = xlo; x <= x1; ++x, cidx += cstep, gout += gstep) {
             // Plane x+2 replaces plane x-2, last read by [A](x-1): every warp finished that before the
             // barrier of iteration x-1, which this thread has passed.
-            if (x > xlo) issue_upto(x + 2);
-            for (; waited <= x + 1 && waited < thi; ++waited) {
-                const int r = waited & (kRing - 1);
-                mbar_wait(sBar + 8 * r, (phases >> r) & 1u);
-                phases ^= 1u << r;
-            }
+            if (x > xlo) issue(x + 2);
+            wait(x + 1);
             const bool do_a = x < xhi;
-            int jnext[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                jnext[s] = -1;
-                if (do_a && x + 1 < xhi && clane) jnext[s] = __ldg(dcode + ((size_t)(x + 1) * wk.M + yy[s]) * kDirs + lane);
-            }
+            int jnext = -1;
+            if (do_a && x + 1 < xhi && lane < S * kDirs) jnext = __ldg(dcode + min(max(cidx + cstep, 0), code_last));
             if (do_a) {
                 const bool store = x >= x0 && x < x1;
                 const uint32_t r0 = (uint32_t)(x & (kRing - 1));
-                const uint32_t n0 = r0 * PLANE_N, p0 = r0 * PLANE_W;
-                const uint32_t nm = x > 0 ? (uint32_t)((x - 1) & (kRing - 1)) * PLANE_N : n0;
-                const uint32_t np = x + 1 < wk.Lx ? (uint32_t)((x + 1) & (kRing - 1)) * PLANE_N : n0;
-                double2 xv[S][kDirs], pv[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    hold_fragments<DIAG>(jvA[s], jheld[s], keep[s], table, dtab, lane);
-                    xv[s][0] = lds_rec(aN[s] + n0);
-                    xv[s][1] = lds_rec(aN[s] + nm);
-                    xv[s][2] = lds_rec(aN[s] + n0 + off_ym[s]);
-                    xv[s][3] = lds_rec(aN[s] + n0 + off_yp[s]);
-                    xv[s][4] = lds_rec(aN[s] + np);
-                    pv[s] = lds_rec(aP[s] + p0);
+                const uint32_t n0 = aN + r0 * PLANE_N, p0 = aP + r0 * PLANE_W;
+                const uint32_t nm = aN + (uint32_t)((x - 1) & (kRing - 1)) * PLANE_N;
+                const uint32_t np = aN + (uint32_t)((x + 1) & (kRing - 1)) * PLANE_N;
+                hold_fragments<DIAG, S>(jvA, jheld, keep, table, dtab, lane);
+                const double2 c_1 = lds_rec(n0 - R), c0 = lds_rec(n0), c1 = lds_rec(n0 + R), c2 = lds_rec(n0 + 2 * R);
+                const double2 m0 = lds_rec(nm), m1 = lds_rec(nm + R);
+                const double2 q0 = lds_rec(np), q1 = lds_rec(np + R);
+                const double2 pv0 = lds_rec(p0), pv1 = lds_rec(p0 + R);
+                double yr0, yi0, yr1, yi1;
+                row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
+                row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
+                const double2 out0 = make_double2(alpha * yr0 - beta * pv0.x, alpha * yi0 - beta * pv0.y);
+                const double2 out1 = make_double2(alpha * yr1 - beta * pv1.x, alpha * yi1 - beta * pv1.y);
+                const uint32_t t1 = a1 + r0 * PLANE_W;
+                sts_rec(t1, out0);
+                sts_rec(t1 + R, out1);
+                tnA[0] = c0;
+                tnA[1] = c1;
+                if (store && owned[0]) {
+                    tc[gout] = out0;
+                    d0 += c0.x * c0.x + c0.y * c0.y;
+                    d1 += out0.x * c0.x + out0.y * c0.y;
                 }
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    double yr, yi;
-                    row_product<DIAG>(xv[s], keep[s], yr, yi);
-                    const double2 out = make_double2(alpha * yr - beta * pv[s].x, alpha * yi - beta * pv[s].y);
-                    sts_rec(a1[s] + p0, out);
-                    tnA[s] = xv[s][0];
-                    if (store && owned[s]) {
-                        tc[((size_t)x * wk.M + yy[s]) * 32 + lane] = out;
-                        d0 += xv[s][0].x * xv[s][0].x + xv[s][0].y * xv[s][0].y;
-                        d1 += out.x * xv[s][0].x + out.y * xv[s][0].y;
-                    }
+                if (store && owned[1]) {
+                    tc[gout + 32] = out1;
+                    d0 += c1.x * c1.x + c1.y * c1.y;
+                    d1 += out1.x * c1.x + out1.y * c1.y;
                 }
             }
             __syncthreads();  // T_{n+1}(x) complete in the ring
             if (x - 1 >= x0) {
                 const int xb1 = x - 1;
-                const uint32_t q0 = (uint32_t)(xb1 & (kRing - 1)) * PLANE_W;
-                const uint32_t qm = xb1 > 0 ? (uint32_t)((xb1 - 1) & (kRing - 1)) * PLANE_W : q0;
-                const uint32_t qp = xb1 + 1 < wk.Lx ? (uint32_t)((xb1 + 1) & (kRing - 1)) * PLANE_W : q0;
-                double2 xv[S][kDirs];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    hold_fragments<DIAG>(jvB[s], jheld[s], keep[s], table, dtab, lane);
-                    xv[s][0] = lds_rec(a1[s] + q0);
-                    xv[s][1] = lds_rec(a1[s] + qm);
-                    // (halo rows compute a dropped result here: keep their reads inside the ring)
-                    xv[s][2] = lds_rec(a1[s] + q0 + (owned[s] ? off_ym[s] : 0u));
-                    xv[s][3] = lds_rec(a1[s] + q0 + (owned[s] ? off_yp[s] : 0u));
-                    xv[s][4] = lds_rec(a1[s] + qp);
+                const uint32_t t0 = a1 + (uint32_t)(xb1 & (kRing - 1)) * PLANE_W;
+                const uint32_t tm = a1 + (uint32_t)((xb1 - 1) & (kRing - 1)) * PLANE_W;
+                const uint32_t tp = a1 + (uint32_t)((xb1 + 1) & (kRing - 1)) * PLANE_W;
+                hold_fragments<DIAG, S>(jvB, jheld, keep, table, dtab, lane);
+                const double2 c_1 = lds_rec(t0 - R), c0 = lds_rec(t0), c1 = lds_rec(t0 + R), c2 = lds_rec(t0 + 2 * R);
+                const double2 m0 = lds_rec(tm), m1 = lds_rec(tm + R);
+                const double2 q0 = lds_rec(tp), q1 = lds_rec(tp + R);
+                double yr0, yi0, yr1, yi1;
+                row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
+                row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
+                const double2 out0 = make_double2(alpha * yr0 - beta * tnB[0].x, alpha * yi0 - beta * tnB[0].y);
+                const double2 out1 = make_double2(alpha * yr1 - beta * tnB[1].x, alpha * yi1 - beta * tnB[1].y);
+                if (owned[0]) {
+                    td[gout - gstep] = out0;
+                    d2 += c0.x * c0.x + c0.y * c0.y;
+                    d3 += out0.x * c0.x + out0.y * c0.y;
                 }
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    double yr, yi;
-                    row_product<DIAG>(xv[s], keep[s], yr, yi);
-                    const double2 out = make_double2(alpha * yr - beta * tnB[s].x, alpha * yi - beta * tnB[s].y);
-                    if (owned[s]) {
-                        td[((size_t)xb1 * wk.M + yy[s]) * 32 + lane] = out;
-                        d2 += xv[s][0].x * xv[s][0].x + xv[s][0].y * xv[s][0].y;
-                        d3 += out.x * xv[s][0].x + out.y * xv[s][0].y;
-                    }
+                if (owned[1]) {
+                    td[gout - gstep + 32] = out1;
+                    d2 += c1.x * c1.x + c1.y * c1.y;
+                    d3 += out1.x * c1.x + out1.y * c1.y;
                 }
             }
+            jvB = jvA;
+            jvA = jnext;
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-                jvB[s] = jvA[s];
-                tnB[s] = tnA[s];
-                jvA[s] = jnext[s];
-            }
+            for (int s = 0; s < S; ++s) tnB[s] = tnA[s];
         }
     }
 
@@ -397,8 +414,8 @@ pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, cons
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
                             double2 *, int, int, double, double, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S> PairKernel pick_pair_shape(bool diag) {
-    return diag ? cheb_pair_step<true, NW, S> : cheb_pair_step<false, NW, S>;
+template <int NW> PairKernel pick_pair_shape(bool diag) {
+    return diag ? cheb_pair_step<true, NW> : cheb_pair_step<false, NW>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -416,13 +433,13 @@ PairShape pair_shape(bool diag) {
     PairShape s;
     if (env_int("BDG_PAIR_WARPS", 8) <= 8) {  // two CTAs per SM: one computes while the other waits at its barrier
         s.warps = 8, s.sites = 2;
-        s.kernel = pick_pair_shape<8, 2>(diag);
+        s.kernel = pick_pair_shape<8>(diag);
     } else {
         s.warps = 16, s.sites = 2;
-        s.kernel = pick_pair_shape<16, 2>(diag);
+        s.kernel = pick_pair_shape<16>(diag);
     }
     const int W = s.warps * s.sites;
-    s.smem = (size_t)kRing * ((W + 2) + 2 * W) * kRecBytes + 64;
+    s.smem = (size_t)kRing * ((W + 2) + 2 * W) * kRecBytes + kRecBytes + 64;
     return s;
 }
 
