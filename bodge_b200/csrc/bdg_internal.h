@@ -81,7 +81,6 @@ struct PairWalk {
     int Lx = 1, M = 1;
     int P = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
-    int l2_ahead = 0;  // planes ahead of the shared-memory loads that are pulled into L2 (0 = off)
 };
 
 // ---- Chebyshev state ----------------------------------------------------------------------

@@ -39,7 +39,8 @@
 namespace {
 
 constexpr int kRecBytes = 512;  // one site record at PW = 8: 8 columns x 4 components x complex128
-constexpr int kRing = 4;        // planes per shared-memory ring (power of two)
+constexpr int kRing = 4;        // planes of the T_{n+1} ring (three read by [B], one being written)
+constexpr int kRingN = 8;       // planes of the T_n ring: three in use, five in flight (power of two)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,12 +74,15 @@ __device__ __forceinline__ double2 lds_rec(uint32_t addr) {
 __device__ __forceinline__ void sts_rec(uint32_t addr, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1,%2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
+
+// T_{n-1}: read exactly once per launch -- do not let it displace anything in L1
+__device__ __forceinline__ double2 ld_prev(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void ld_table_pred(double &v, const double *p, unsigned take) {
     asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(v) : "l"(p), "r"(take));
-}
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
 }
 
 constexpr int kDirs = 5;  // direction-ordered row: self, x-1, y-1, y+1, x+1 (= ascending block column)
@@ -159,15 +163,14 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
                double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
-               double alpha, double beta, double *__restrict__ partials, unsigned *__restrict__ tickets,
+               double alpha, double *__restrict__ partials, unsigned *__restrict__ tickets,
                double *__restrict__ dots_step, const PairWalk wk) {
     constexpr int S = 2, W = NW * S, R = kRecBytes;
     constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
     extern __shared__ __align__(128) unsigned char pair_smem[];
     const uint32_t sTn = smem_u32(pair_smem);         // T_n planes, local site l2 = y - (y0 - 2)
-    const uint32_t sTp = sTn + kRing * PLANE_N;       // T_{n-1} planes, local site l = y - (y0 - 1)
-    const uint32_t sT1 = sTp + kRing * PLANE_W;       // T_{n+1} planes (computed here), local site l
-    const uint32_t sBar = sT1 + kRing * PLANE_W + R;  // guard record (halo rows of [B] read one past the ring), then one mbarrier per slot
+    const uint32_t sT1 = sTn + kRingN * PLANE_N + R;  // guard record, then T_{n+1} planes (computed here), local site l = y - (y0 - 1)
+    const uint32_t sBar = sT1 + kRing * PLANE_W + R;  // guard record (halo rows of [B] read one before / past the ring), then one mbarrier per T_n slot
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int panel = blockIdx.y;
@@ -177,15 +180,14 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const int l0 = S * warp;  // this warp's sites: l0, l0 + 1
     // own-record addresses of site l0 in slot 0 of each ring (+ lane's 16 bytes)
     uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
-    uint32_t aP = sTp + (uint32_t)l0 * R + (uint32_t)lane * 16u;
     uint32_t a1 = sT1 + (uint32_t)l0 * R + (uint32_t)lane * 16u;
-    pin(aN), pin(aP), pin(a1);
+    pin(aN), pin(a1);
 
-    for (uint32_t o = threadIdx.x * 16u; o < kRing * (PLANE_N + 2 * PLANE_W) + R; o += NW * 32 * 16u)
+    for (uint32_t o = threadIdx.x * 16u; o < kRingN * PLANE_N + kRing * PLANE_W + 2 * R; o += NW * 32 * 16u)
         sts_rec(sTn + o, make_double2(0.0, 0.0));
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int r = 0; r < kRing; ++r) mbar_init(sBar + 8 * r, 1);
+        for (int r = 0; r < kRingN; ++r) mbar_init(sBar + 8 * r, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
@@ -207,40 +209,27 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         const int xlo = max(0, x0 - 1), xhi = min(wk.Lx, x1 + 1);    // planes of sub-step [A]
         const int tlo = max(0, xlo - 1), thi = min(wk.Lx, xhi + 1);  // T_n planes they read
         const int nlo = max(0, y0 - 2), nhi = min(wk.M, y0 + wk.P + 2);  // in-plane run of T_n
-        const int plo = max(0, y0 - 1), phi = min(wk.M, y0 + wk.P + 1);  // ... of T_{n-1}
 
-        // Plane q -> ring slot q % kRing: T_n always, T_{n-1} when [A] runs on it; one barrier phase.
+        // T_n plane q -> ring slot q % kRingN, one barrier phase per plane.
         auto issue = [&](int q) {
             if (threadIdx.x == 0 && q < thi) {
-                const int r = q & (kRing - 1);
-                const bool with_prev = q >= xlo && q < xhi;
+                const int r = q & (kRingN - 1);
                 const uint32_t nbytes = (uint32_t)(nhi - nlo) * R;
-                const uint32_t pbytes = with_prev ? (uint32_t)(phi - plo) * R : 0u;
-                mbar_expect_tx(sBar + 8 * r, nbytes + pbytes);
+                mbar_expect_tx(sBar + 8 * r, nbytes);
                 bulk_g2s(sTn + r * PLANE_N + (uint32_t)(nlo - (y0 - 2)) * R, tb + ((size_t)q * wk.M + nlo) * 32, nbytes,
                          sBar + 8 * r);
-                if (with_prev)
-                    bulk_g2s(sTp + r * PLANE_W + (uint32_t)(plo - (y0 - 1)) * R, ta + ((size_t)q * wk.M + plo) * 32, pbytes,
-                             sBar + 8 * r);
-                // ... and pull the planes a few iterations further on into L2
-                const int far = q + wk.l2_ahead;
-                if (wk.l2_ahead > 0 && far < thi) {
-                    bulk_prefetch_l2(tb + ((size_t)far * wk.M + nlo) * 32, nbytes);
-                    if (far < xhi) bulk_prefetch_l2(ta + ((size_t)far * wk.M + plo) * 32, (uint32_t)(phi - plo) * R);
-                }
             }
         };
         auto wait = [&](int q) {
             if (q < thi) {
-                const int r = q & (kRing - 1);
+                const int r = q & (kRingN - 1);
                 mbar_wait(sBar + 8 * r, (phases >> r) & 1u);
                 phases ^= 1u << r;
             }
         };
 
         __syncthreads();  // every warp is done with the previous item's planes
-        for (int q = tlo; q <= xlo + 2; ++q) issue(q);
-        for (int q = tlo; q <= xlo; ++q) wait(q);
+        for (int q = tlo; q <= xlo + kRingN - 3; ++q) issue(q);
 
         // Site l0 + s of this warp: y = y0 - 1 + l0 + s.  Owned = inside the patch and the lattice.
         const int ya = y0 - 1 + l0;
@@ -254,39 +243,45 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         if (lane < S * kDirs) jvA = __ldg(dcode + min(max(cidx, 0), code_last));
         size_t gout = ((size_t)xlo * wk.M + ya) * 32 + lane;  // T_{n+1}(x, ya); the second row 32 elements on
         const size_t gstep = (size_t)wk.M * 32;
-        double2 tnA[S], tnB[S];
+        // T_{n-1} of the warp's two rows goes straight to registers, one plane ahead (read once, by
+        // this warp only: nothing to share through shared memory).
+        bool prev_ok[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) tnA[s] = tnB[s] = make_double2(0.0, 0.0);
+        for (int s = 0; s < S; ++s) prev_ok[s] = l0 + s < wk.P + 2 && ya + s >= 0 && ya + s < wk.M;
+        double2 pvn0 = make_double2(0.0, 0.0), pvn1 = make_double2(0.0, 0.0);
+        if (prev_ok[0]) pvn0 = ld_prev(ta + gout);
+        if (prev_ok[1]) pvn1 = ld_prev(ta + gout + 32);
+        for (int q = tlo; q <= xlo; ++q) wait(q);
 
         for (int x = xlo; x <= x1; ++x, cidx += cstep, gout += gstep) {
-            // Plane x+2 replaces plane x-2, last read by [A](x-1): every warp finished that before the
-            // barrier of iteration x-1, which this thread has passed.
-            if (x > xlo) issue(x + 2);
+            // Plane x + kRingN - 3 replaces plane x - 3, last read by [A](x-2).
+            if (x > xlo) issue(x + kRingN - 3);
+            const double2 pv0 = pvn0, pv1 = pvn1;
+            if (x + 1 < xhi) {
+                if (prev_ok[0]) pvn0 = ld_prev(ta + gout + gstep);
+                if (prev_ok[1]) pvn1 = ld_prev(ta + gout + gstep + 32);
+            }
             wait(x + 1);
             const bool do_a = x < xhi;
             int jnext = -1;
             if (do_a && x + 1 < xhi && lane < S * kDirs) jnext = __ldg(dcode + min(max(cidx + cstep, 0), code_last));
             if (do_a) {
                 const bool store = x >= x0 && x < x1;
-                const uint32_t r0 = (uint32_t)(x & (kRing - 1));
-                const uint32_t n0 = aN + r0 * PLANE_N, p0 = aP + r0 * PLANE_W;
-                const uint32_t nm = aN + (uint32_t)((x - 1) & (kRing - 1)) * PLANE_N;
-                const uint32_t np = aN + (uint32_t)((x + 1) & (kRing - 1)) * PLANE_N;
+                const uint32_t n0 = aN + (uint32_t)(x & (kRingN - 1)) * PLANE_N;
+                const uint32_t nm = aN + (uint32_t)((x - 1) & (kRingN - 1)) * PLANE_N;
+                const uint32_t np = aN + (uint32_t)((x + 1) & (kRingN - 1)) * PLANE_N;
                 hold_fragments<DIAG, S>(jvA, jheld, keep, table, dtab, lane);
                 const double2 c_1 = lds_rec(n0 - R), c0 = lds_rec(n0), c1 = lds_rec(n0 + R), c2 = lds_rec(n0 + 2 * R);
                 const double2 m0 = lds_rec(nm), m1 = lds_rec(nm + R);
                 const double2 q0 = lds_rec(np), q1 = lds_rec(np + R);
-                const double2 pv0 = lds_rec(p0), pv1 = lds_rec(p0 + R);
                 double yr0, yi0, yr1, yi1;
                 row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
                 row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
-                const double2 out0 = make_double2(alpha * yr0 - beta * pv0.x, alpha * yi0 - beta * pv0.y);
-                const double2 out1 = make_double2(alpha * yr1 - beta * pv1.x, alpha * yi1 - beta * pv1.y);
-                const uint32_t t1 = a1 + r0 * PLANE_W;
+                const double2 out0 = make_double2(fma(alpha, yr0, -pv0.x), fma(alpha, yi0, -pv0.y));
+                const double2 out1 = make_double2(fma(alpha, yr1, -pv1.x), fma(alpha, yi1, -pv1.y));
+                const uint32_t t1 = a1 + (uint32_t)(x & (kRing - 1)) * PLANE_W;
                 sts_rec(t1, out0);
                 sts_rec(t1 + R, out1);
-                tnA[0] = c0;
-                tnA[1] = c1;
                 if (store && owned[0]) {
                     tc[gout] = out0;
                     d0 += c0.x * c0.x + c0.y * c0.y;
@@ -308,11 +303,14 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const double2 c_1 = lds_rec(t0 - R), c0 = lds_rec(t0), c1 = lds_rec(t0 + R), c2 = lds_rec(t0 + 2 * R);
                 const double2 m0 = lds_rec(tm), m1 = lds_rec(tm + R);
                 const double2 q0 = lds_rec(tp), q1 = lds_rec(tp + R);
+                // T_n(x-1) of the two rows: its plane stays in the T_n ring until iteration x+2 issues over it
+                const uint32_t nb = aN + (uint32_t)(xb1 & (kRingN - 1)) * PLANE_N;
+                const double2 tn0 = lds_rec(nb), tn1 = lds_rec(nb + R);
                 double yr0, yi0, yr1, yi1;
                 row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
                 row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
-                const double2 out0 = make_double2(alpha * yr0 - beta * tnB[0].x, alpha * yi0 - beta * tnB[0].y);
-                const double2 out1 = make_double2(alpha * yr1 - beta * tnB[1].x, alpha * yi1 - beta * tnB[1].y);
+                const double2 out0 = make_double2(fma(alpha, yr0, -tn0.x), fma(alpha, yi0, -tn0.y));
+                const double2 out1 = make_double2(fma(alpha, yr1, -tn1.x), fma(alpha, yi1, -tn1.y));
                 if (owned[0]) {
                     td[gout - gstep] = out0;
                     d2 += c0.x * c0.x + c0.y * c0.y;
@@ -326,8 +324,6 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             }
             jvB = jvA;
             jvA = jnext;
-#pragma unroll
-            for (int s = 0; s < S; ++s) tnB[s] = tnA[s];
         }
     }
 
@@ -412,7 +408,7 @@ pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, cons
 }
 
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
-                            double2 *, int, int, double, double, double *, unsigned *, double *, const PairWalk);
+                            double2 *, int, int, double, double *, unsigned *, double *, const PairWalk);
 
 template <int NW> PairKernel pick_pair_shape(bool diag) {
     return diag ? cheb_pair_step<true, NW> : cheb_pair_step<false, NW>;
@@ -439,7 +435,7 @@ PairShape pair_shape(bool diag) {
         s.kernel = pick_pair_shape<16>(diag);
     }
     const int W = s.warps * s.sites;
-    s.smem = (size_t)kRing * ((W + 2) + 2 * W) * kRecBytes + kRecBytes + 64;
+    s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * kRingN;
     return s;
 }
 
@@ -512,7 +508,6 @@ int pair_configure(bdg_system *sys) {
         }
         if (forced > 0) break;
     }
-    w.l2_ahead = std::max(0, env_int("BDG_PAIR_L2_AHEAD", 0));
     st.pair_grid_x = (int)std::min<int64_t>(slots, w.n_items);
     return BDG_OK;
 }
@@ -526,7 +521,7 @@ int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev), static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1),
-        static_cast<double2 *>(x_next2), (int)e.n_sites, st.n_panels, 2.0 / st.scale, 1.0, st.partials.as<double>(),
+        static_cast<double2 *>(x_next2), (int)e.n_sites, st.n_panels, 2.0 / st.scale, st.partials.as<double>(),
         st.tickets.as<unsigned>(), dots_step, st.pair_walk);
     BDG_CUDA(cudaGetLastError());
     return BDG_OK;
