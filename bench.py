@@ -377,8 +377,8 @@ def run_ours(args):
     moved = moved_step * K / (kernel_ms * 1e-3) / 1e9
     step_launches = max(launches - 1, 1)   # `launches` also counts the moment read-out kernel
     steps_per_launch = K / step_launches
-    kernel_name = {"pair": "cheb_pair_step (two steps per launch: block-dictionary matrix, T_n / T_{n-1} planes staged by "
-                           "TMA bulk copies, T_{n+1} kept in shared memory)",
+    kernel_name = {"pair": "cheb_pair_step (two steps per launch: block-dictionary matrix, T_n planes staged in shared memory by "
+                           "TMA bulk copies, T_{n-1} straight to registers, T_{n+1} kept in shared memory)",
                    "dict": "cheb_step_ell<DICT> (block-dictionary matrix)",
                    "dict_diag": "cheb_step_ell<DICT,DIAG> (block-dictionary matrix, real-diagonal hopping blocks by DFMA)",
                    "ell": "cheb_step_ell",

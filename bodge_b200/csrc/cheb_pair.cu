@@ -11,15 +11,16 @@
 // Geometry.  Lattices whose x-planes are one-dimensional (Lz = 1 or Ly = 1; M = sites per plane).
 // The plane is cut into patches of P owned sites; a CTA marches one patch along a segment of x:
 //
-//   iteration x:  [A] T_{n+1}(x, y) for the P owned sites AND one halo site on either side,
-//                     from T_n planes x-1, x, x+1 (P + 4 sites each) and T_{n-1} plane x (P + 2),
-//                     all staged in shared memory by bulk async copies (TMA, cp.async.bulk, one
-//                     contiguous 17 KB run per plane, two planes ahead, completion on an mbarrier);
+//   iteration x:  [A] T_{n+1}(x, y) for the P owned sites AND one halo site on either side, from
+//                     T_n planes x-1, x, x+1 (P + 4 sites each), staged in a shared-memory ring of 8
+//                     planes by bulk async copies (TMA: cp.async.bulk, one contiguous 9 KB run per
+//                     plane, five planes ahead, completion on an mbarrier), and T_{n-1}(x, y), which
+//                     only this warp reads: straight to registers, one plane ahead;
 //                     the result goes to a shared-memory ring (4 planes) and, for owned sites of
 //                     owned planes, to HBM;
 //                 __syncthreads
-//                 [B] T_{n+2}(x-1, y) for the owned sites from the ring's planes x-2, x-1, x
-//                     (the T_n record of the site itself is still in registers from [A](x-1)).
+//                 [B] T_{n+2}(x-1, y) for the owned sites from the T_{n+1} ring's planes x-2, x-1, x
+//                     (T_n(x-1, y) is still in the T_n ring).
 //
 // The halo T_{n+1} values (one site either side in y, one plane either side of the segment in x)
 // are recomputed, not exchanged: (P+2)/P x (len+2)/len redundant work on sub-step [A], no

@@ -110,7 +110,8 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
  *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
-/* AUTO = DICT_DIAG, else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+/* AUTO = PAIR where its DFMA variant applies (DICT_DIAG matrix, open 2-D stencil, >= 5 columns), else DICT_DIAG,
+ *        else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
  * PAIR = two recursion steps per launch on the DICT / DICT_DIAG format: T_{n+1} is consumed out of shared
  *        memory instead of coming back from HBM, so two steps move four vector passes instead of six.  Needs
  *        >= 5 columns and a lattice with one-dimensional x-planes (Lz = 1 or Ly = 1) whose stored blocks form
