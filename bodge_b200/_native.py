@@ -34,6 +34,7 @@ SIGNATURES = {
     "bdg_abi_version": [],
     "bdg_device_count": [C.POINTER(C.c_int)],
     "bdg_destroy": [_vp],
+    "bdg_release_cached": [C.c_int],
     "bdg_set_stream": [_vp, _vp],
     "bdg_sync": [_vp],
     "bdg_device_bytes": [_vp, _i64p],
@@ -105,6 +106,11 @@ _EXC = {
 def check(rc: int):
     if rc != OK:
         raise _EXC.get(rc, RuntimeError)(last_error())
+
+
+def release_cached(device: int = 0) -> None:
+    """Return the library's cache of released device buffers (>= 1 MiB each) to the CUDA driver."""
+    check(load().bdg_release_cached(int(device)))
 
 
 def device_count() -> int:

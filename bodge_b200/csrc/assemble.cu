@@ -6,7 +6,10 @@
 // 16-byte block element with coalesced 128-bit accesses; nothing here is GEMM shaped.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "bdg_internal.h"
 
@@ -22,23 +25,92 @@ void bdg_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// Large device buffers are recycled through a per-device cache: cudaMalloc / cudaFree of the 1.3 GB
+// block array cost milliseconds each (page-table work), which is what creating or destroying a
+// 10^6-site Hamiltonian spent most of its time on.  BDG_CACHE_MB bounds the bytes held (0 = off).
+namespace {
+constexpr int kMaxDevices = 16;
+constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+std::mutex g_cache_mutex;
+std::multimap<size_t, void *> g_cache[kMaxDevices];
+size_t g_cache_bytes[kMaxDevices] = {};
+std::vector<void *> g_host_pages;  // pinned sizeof(Scalars) pages of destroyed handles
+
+size_t cache_limit() {
+    const char *v = getenv("BDG_CACHE_MB");
+    return (size_t)(v && *v ? atoll(v) : 8192) << 20;
+}
+
+void *cache_take(int device, size_t bytes, size_t *got) {
+    if (device < 0 || device >= kMaxDevices || bytes < kCacheMinBytes) return nullptr;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    auto it = g_cache[device].lower_bound(bytes);
+    if (it == g_cache[device].end() || it->first > bytes + bytes / 4) return nullptr;
+    void *ptr = it->second;
+    *got = it->first;
+    g_cache_bytes[device] -= it->first;
+    g_cache[device].erase(it);
+    return ptr;
+}
+
+bool cache_put(int device, void *ptr, size_t bytes) {
+    if (device < 0 || device >= kMaxDevices || bytes < kCacheMinBytes) return false;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (g_cache_bytes[device] + bytes > cache_limit()) return false;
+    g_cache[device].emplace(bytes, ptr);
+    g_cache_bytes[device] += bytes;
+    return true;
+}
+
+void cache_flush(int device) {
+    if (device < 0 || device >= kMaxDevices) return;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto &kv : g_cache[device]) cudaFree(kv.second);
+    g_cache[device].clear();
+    g_cache_bytes[device] = 0;
+}
+}  // namespace
+
 int dev_alloc(bdg_system *sys, DevBuf &buf, size_t bytes) {
     if (buf.ptr && buf.bytes >= bytes) return BDG_OK;
     dev_free(sys, buf);
     if (bytes == 0) bytes = 16;
-    BDG_CUDA(cudaMalloc(&buf.ptr, bytes));
-    buf.bytes = bytes;
-    sys->dev_bytes += (int64_t)bytes;
+    size_t got = bytes;
+    void *ptr = cache_take(sys->device, bytes, &got);
+    if (!ptr) {
+        cudaError_t err = cudaMalloc(&ptr, bytes);
+        if (err == cudaErrorMemoryAllocation) {  // give the cached buffers back to the driver and retry
+            cudaGetLastError();
+            cache_flush(sys->device);
+            err = cudaMalloc(&ptr, bytes);
+        }
+        BDG_CUDA(err);
+    }
+    buf.ptr = ptr;
+    buf.bytes = got;
+    sys->dev_bytes += (int64_t)got;
     return BDG_OK;
 }
 
 void dev_free(bdg_system *sys, DevBuf &buf) {
     if (buf.ptr) {
-        cudaFree(buf.ptr);
         sys->dev_bytes -= (int64_t)buf.bytes;
+        bool cached = false;
+        if (buf.bytes >= kCacheMinBytes) {
+            // cudaFree would wait for the device; a recycled buffer must at least not be in use on this stream
+            cudaStreamSynchronize(sys->stream);
+            cached = cache_put(sys->device, buf.ptr, buf.bytes);
+        }
+        if (!cached) cudaFree(buf.ptr);
     }
     buf.ptr = nullptr;
     buf.bytes = 0;
+}
+
+extern "C" int bdg_release_cached(int device) {
+    BDG_CUDA(cudaSetDevice(device));
+    cache_flush(device);
+    return BDG_OK;
 }
 
 int ensure_scratch(bdg_system *sys, int which, size_t bytes) { return dev_alloc(sys, sys->scratch_i32[which], bytes); }
@@ -70,14 +142,19 @@ static int create_common(int device, bdg_system **out) {
     BDG_CUDA(cudaSetDevice(device));
     bdg_system *sys = new bdg_system();
     sys->device = device;
-    cudaDeviceProp prop;
-    BDG_CUDA(cudaGetDeviceProperties(&prop, device));
-    sys->sm_count = prop.multiProcessorCount;
+    BDG_CUDA(cudaDeviceGetAttribute(&sys->sm_count, cudaDevAttrMultiProcessorCount, device));  // (cudaGetDeviceProperties takes milliseconds)
     BDG_CUDA(cudaStreamCreateWithFlags(&sys->own_stream, cudaStreamNonBlocking));
     sys->stream = sys->own_stream;
     int rc = dev_alloc(sys, sys->scalars, sizeof(Scalars));
     if (rc != BDG_OK) return rc;
-    BDG_CUDA(cudaMallocHost(&sys->host_scalars, sizeof(Scalars)));
+    {   // pinned pages are expensive to create: recycle them like the device buffers
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (!g_host_pages.empty()) {
+            sys->host_scalars = g_host_pages.back();
+            g_host_pages.pop_back();
+        }
+    }
+    if (!sys->host_scalars) BDG_CUDA(cudaMallocHost(&sys->host_scalars, sizeof(Scalars)));
     *out = sys;
     return BDG_OK;
 }
@@ -110,7 +187,10 @@ extern "C" int bdg_destroy(bdg_t *sys) {
     for (auto &b : sys->scratch_i32) dev_free(sys, b);
     for (auto &b : sys->stage) dev_free(sys, b);
     dev_free(sys, sys->scalars);
-    if (sys->host_scalars) cudaFreeHost(sys->host_scalars);
+    if (sys->host_scalars) {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        g_host_pages.push_back(sys->host_scalars);
+    }
     if (sys->own_stream) cudaStreamDestroy(sys->own_stream);
     delete sys;
     return BDG_OK;

@@ -43,6 +43,11 @@ int bdg_abi_version(void);
 const char *bdg_last_error(void);
 int bdg_device_count(int *count);
 int bdg_destroy(bdg_t *sys);
+/* Device buffers of >= 1 MiB released by a handle are kept in a per-device cache and handed to the next
+ * handle that asks for that size (cudaMalloc / cudaFree of a 1.3 GB block array cost milliseconds; the
+ * reference has no counterpart -- numpy's allocator plays this role for its `_matrix.data`).  At most
+ * BDG_CACHE_MB (default 8192, 0 = off) are held; this returns them to the driver. */
+int bdg_release_cached(int device);
 /* Borrow a CUDA stream (cudaStream_t / CUstream as void*); NULL restores the handle's own. */
 int bdg_set_stream(bdg_t *sys, void *stream);
 int bdg_sync(bdg_t *sys);
