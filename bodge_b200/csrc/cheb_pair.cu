@@ -149,8 +149,9 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
 }
 
 // NW warps per CTA, two ADJACENT sites per warp and plane: W = 2 NW sites per plane in sub-step [A]
-// (P <= W - 2 of them owned).  Dynamic shared memory: kRing x ((W + 2) + W + W) records + a guard
-// record + barriers.
+// (P <= W - 2 of them owned).  Dynamic shared memory: kRingN planes of W + 2 records (T_n), kRing
+// planes of W records (T_{n+1}), two guard records, one mbarrier per T_n plane: 105 KB at NW = 8, so two
+// CTAs share an SM (one computes while the other waits at its barrier).
 //
 // The matrix arrives as `dcode[row][5]`: the dictionary code of the row's block in each stencil
 // direction (self, x-1, y-1, y+1, x+1; -1 = none), so the records a row needs sit at fixed offsets from
