@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C5] [--cols 8]
 
-One "step" = one pass of the fused kernel T_{n+1} = 2 H~ T_n - T_{n-1} (+ the two moment dot
-products) over one tile of ``cols`` vectors (default 8) per GPU, i.e. one HBM pass over the
-matrix and the vectors.  Workload: BASELINE.json config C5, CubicLattice((1000,1000,1))
+One "step" = one recursion step T_{n+1} = 2 H~ T_n - T_{n-1} (+ the two moment dot products) over one
+tile of ``cols`` vectors (default 8) per GPU.  The single-step kernels make one HBM pass over the
+matrix and the vectors per step; the default kernel on this workload (``pair``) does TWO steps per
+launch, so K steps are K/2 launches (``gpu_launches``, ``roofline.steps_per_launch``).  Workload: BASELINE.json config C5, CubicLattice((1000,1000,1))
 altermagnet/superconductor Josephson junction, 10^6 sites, 4,996,000 BSR blocks, synthetic
 (SURVEY 8d).  N > 1: one process per GPU (torchrun), a replica of the matrix and its own 8 columns
 on every GPU (weak scaling), one NCCL all-reduce of the moments at the end of the timed region.
