@@ -160,14 +160,14 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
 // all the same and meets a zero fragment: the rings are cleared once, so whatever sits there is an
 // earlier, finite, vector value.  Warps whose site does not exist (ragged last patch) compute on
 // whatever the rings hold and store nothing: the row body has no branches.
-template <bool DIAG, int NW>
-__global__ void __launch_bounds__(NW * 32, 16 / NW)
+template <bool DIAG, int NW, int S, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
                double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
                double alpha, double *__restrict__ partials, unsigned *__restrict__ tickets,
                double *__restrict__ dots_step, const PairWalk wk) {
-    constexpr int S = 2, W = NW * S, R = kRecBytes;
+    constexpr int W = NW * S, R = kRecBytes;
     constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
     extern __shared__ __align__(128) unsigned char pair_smem[];
     const uint32_t sTn = smem_u32(pair_smem);         // T_n planes, local site l2 = y - (y0 - 2)
@@ -250,18 +250,22 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         bool prev_ok[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) prev_ok[s] = l0 + s < wk.P + 2 && ya + s >= 0 && ya + s < wk.M;
-        double2 pvn0 = make_double2(0.0, 0.0), pvn1 = make_double2(0.0, 0.0);
-        if (prev_ok[0]) pvn0 = ld_prev(ta + gout);
-        if (prev_ok[1]) pvn1 = ld_prev(ta + gout + 32);
+        double2 pvn[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            pvn[s] = make_double2(0.0, 0.0);
+            if (prev_ok[s]) pvn[s] = ld_prev(ta + gout + 32 * s);
+        }
         for (int q = tlo; q <= xlo; ++q) wait(q);
 
         for (int x = xlo; x <= x1; ++x, cidx += cstep, gout += gstep) {
             // Plane x + kRingN - 3 replaces plane x - 3, last read by [A](x-2).
             if (x > xlo) issue(x + kRingN - 3);
-            const double2 pv0 = pvn0, pv1 = pvn1;
-            if (x + 1 < xhi) {
-                if (prev_ok[0]) pvn0 = ld_prev(ta + gout + gstep);
-                if (prev_ok[1]) pvn1 = ld_prev(ta + gout + gstep + 32);
+            double2 pv[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                pv[s] = pvn[s];
+                if (x + 1 < xhi && prev_ok[s]) pvn[s] = ld_prev(ta + gout + gstep + 32 * s);
             }
             wait(x + 1);
             const bool do_a = x < xhi;
@@ -273,26 +277,28 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t nm = aN + (uint32_t)((x - 1) & (kRingN - 1)) * PLANE_N;
                 const uint32_t np = aN + (uint32_t)((x + 1) & (kRingN - 1)) * PLANE_N;
                 hold_fragments<DIAG, S>(jvA, jheld, keep, table, dtab, lane);
-                const double2 c_1 = lds_rec(n0 - R), c0 = lds_rec(n0), c1 = lds_rec(n0 + R), c2 = lds_rec(n0 + 2 * R);
-                const double2 m0 = lds_rec(nm), m1 = lds_rec(nm + R);
-                const double2 q0 = lds_rec(np), q1 = lds_rec(np + R);
-                double yr0, yi0, yr1, yi1;
-                row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
-                row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
-                const double2 out0 = make_double2(fma(alpha, yr0, -pv0.x), fma(alpha, yi0, -pv0.y));
-                const double2 out1 = make_double2(fma(alpha, yr1, -pv1.x), fma(alpha, yi1, -pv1.y));
+                double2 c[S + 2], m[S], q[S], out[S];  // c[1 + s] = the own record of site s; c[0], c[S + 1] = the warp's in-plane neighbours
+#pragma unroll
+                for (int i = 0; i < S + 2; ++i) c[i] = lds_rec(n0 + (uint32_t)(i - 1) * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) m[s] = lds_rec(nm + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) q[s] = lds_rec(np + (uint32_t)s * R);
                 const uint32_t t1 = a1 + (uint32_t)(x & (kRing - 1)) * PLANE_W;
-                sts_rec(t1, out0);
-                sts_rec(t1 + R, out1);
-                if (store && owned[0]) {
-                    tc[gout] = out0;
-                    d0 += c0.x * c0.x + c0.y * c0.y;
-                    d1 += out0.x * c0.x + out0.y * c0.y;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double yr, yi;
+                    row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
+                    out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
+                    sts_rec(t1 + (uint32_t)s * R, out[s]);
                 }
-                if (store && owned[1]) {
-                    tc[gout + 32] = out1;
-                    d0 += c1.x * c1.x + c1.y * c1.y;
-                    d1 += out1.x * c1.x + out1.y * c1.y;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (store && owned[s]) {
+                        tc[gout + 32 * s] = out[s];
+                        d0 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
+                        d1 += out[s].x * c[1 + s].x + out[s].y * c[1 + s].y;
+                    }
                 }
             }
             __syncthreads();  // T_{n+1}(x) complete in the ring
@@ -302,26 +308,27 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t tm = a1 + (uint32_t)((xb1 - 1) & (kRing - 1)) * PLANE_W;
                 const uint32_t tp = a1 + (uint32_t)((xb1 + 1) & (kRing - 1)) * PLANE_W;
                 hold_fragments<DIAG, S>(jvB, jheld, keep, table, dtab, lane);
-                const double2 c_1 = lds_rec(t0 - R), c0 = lds_rec(t0), c1 = lds_rec(t0 + R), c2 = lds_rec(t0 + 2 * R);
-                const double2 m0 = lds_rec(tm), m1 = lds_rec(tm + R);
-                const double2 q0 = lds_rec(tp), q1 = lds_rec(tp + R);
-                // T_n(x-1) of the two rows: its plane stays in the T_n ring until iteration x+2 issues over it
+                double2 c[S + 2], m[S], q[S], tn[S];
+#pragma unroll
+                for (int i = 0; i < S + 2; ++i) c[i] = lds_rec(t0 + (uint32_t)(i - 1) * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                // T_n(x-1) of the warp's rows: its plane stays in the T_n ring until iteration x+2 issues over it
                 const uint32_t nb = aN + (uint32_t)(xb1 & (kRingN - 1)) * PLANE_N;
-                const double2 tn0 = lds_rec(nb), tn1 = lds_rec(nb + R);
-                double yr0, yi0, yr1, yi1;
-                row_product<DIAG>(c0, m0, c_1, c1, q0, keep[0], yr0, yi0);
-                row_product<DIAG>(c1, m1, c0, c2, q1, keep[1], yr1, yi1);
-                const double2 out0 = make_double2(fma(alpha, yr0, -tn0.x), fma(alpha, yi0, -tn0.y));
-                const double2 out1 = make_double2(fma(alpha, yr1, -tn1.x), fma(alpha, yi1, -tn1.y));
-                if (owned[0]) {
-                    td[gout - gstep] = out0;
-                    d2 += c0.x * c0.x + c0.y * c0.y;
-                    d3 += out0.x * c0.x + out0.y * c0.y;
-                }
-                if (owned[1]) {
-                    td[gout - gstep + 32] = out1;
-                    d2 += c1.x * c1.x + c1.y * c1.y;
-                    d3 += out1.x * c1.x + out1.y * c1.y;
+#pragma unroll
+                for (int s = 0; s < S; ++s) tn[s] = lds_rec(nb + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double yr, yi;
+                    row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
+                    const double2 out = make_double2(fma(alpha, yr, -tn[s].x), fma(alpha, yi, -tn[s].y));
+                    if (owned[s]) {
+                        td[gout - gstep + 32 * s] = out;
+                        d2 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
+                        d3 += out.x * c[1 + s].x + out.y * c[1 + s].y;
+                    }
                 }
             }
             jvB = jvA;
@@ -412,8 +419,8 @@ pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, cons
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
                             double2 *, int, int, double, double *, unsigned *, double *, const PairWalk);
 
-template <int NW> PairKernel pick_pair_shape(bool diag) {
-    return diag ? cheb_pair_step<true, NW> : cheb_pair_step<false, NW>;
+template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag) {
+    return diag ? cheb_pair_step<true, NW, S, MINB> : cheb_pair_step<false, NW, S, MINB>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -429,13 +436,13 @@ struct PairShape {
 
 PairShape pair_shape(bool diag) {
     PairShape s;
-    if (env_int("BDG_PAIR_WARPS", 8) <= 8) {  // two CTAs per SM: one computes while the other waits at its barrier
-        s.warps = 8, s.sites = 2;
-        s.kernel = pick_pair_shape<8>(diag);
-    } else {
-        s.warps = 16, s.sites = 2;
-        s.kernel = pick_pair_shape<16>(diag);
-    }
+    // 8 warps x 2 sites: two CTAs per SM, one computes while the other waits at its barrier.  The shape
+    // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
+    // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
+    if (env_int("BDG_PAIR_WARPS", 8) <= 8)
+        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag);
+    else
+        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag);
     const int W = s.warps * s.sites;
     s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * kRingN;
     return s;
