@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--cols", type=int, default=8, help="vector columns per GPU (weak scaling, the default)")
     ap.add_argument("--total-cols", type=int, default=0,
                     help="strong scaling instead: this many columns in total, split evenly over the GPUs (SURVEY 8e: 64)")
-    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--kernel", default="auto_moments",
+                    help="auto_moments = what chebyshev_moments / free_energy / ldos use (only moments are read)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-plain", action="store_true", help="skip the uncompressed-matrix comparison run")
@@ -324,7 +325,7 @@ def run_ours(args):
     # The same steps on the uncompressed fixed-width matrix copy (every block read from HBM): shows
     # what the block dictionary buys and how close the plain kernel runs to the HBM roofline.
     plain = None
-    if (fmt["kernel"].startswith("dict") or fmt["kernel"] == "pair") and not args.no_plain:
+    if (fmt["kernel"].startswith("dict") or fmt["kernel"] in ("pair", "t2")) and not args.no_plain:
         p_total, p_kernel, _, _, p_fmt = timed_steps("ell")
         plain = {"kernel": "cheb_step_ell (every block from HBM)", "kernel_ms_per_launch": p_kernel / K,
                  "steps_per_s": world * K / (p_total * 1e-3), "matrix_bytes_per_launch": p_fmt["matrix_bytes_per_step"]}
@@ -374,11 +375,15 @@ def run_ours(args):
     bytes_step = info["bytes_per_step"]
     achieved = bytes_step * K / (kernel_ms * 1e-3) / 1e9
     # per step: three vector passes; the pair kernel (two steps per launch) moves four per two steps
-    moved_step = fmt["matrix_bytes_per_step"] + (128 if fmt["kernel"] == "pair" else 192) * n_sites * cols
+    # (the even-vector recursion "t2" moves three per two steps)
+    moved_step = fmt["matrix_bytes_per_step"] + {"pair": 128, "t2": 96}.get(fmt["kernel"], 192) * n_sites * cols
     moved = moved_step * K / (kernel_ms * 1e-3) / 1e9
     step_launches = max(launches - 1, 1)   # `launches` also counts the moment read-out kernel
     steps_per_launch = K / step_launches
-    kernel_name = {"pair": "cheb_pair_step (two steps per launch: block-dictionary matrix, T_n planes staged in shared memory by "
+    kernel_name = {"t2": "cheb_pair_step<MODE=T2> (two applications of H~ per launch on the even vectors E_j = T_2j x: "
+                         "E_{j+1} = 2 T_2(H~) E_j - E_{j-1}; block-dictionary matrix, E_j planes staged in shared memory by TMA "
+                         "bulk copies, H~ E_j kept in shared memory, E_{j+1} written over E_{j-1})",
+                   "pair": "cheb_pair_step (two steps per launch: block-dictionary matrix, T_n planes staged in shared memory by "
                            "TMA bulk copies, T_{n-1} straight to registers, T_{n+1} kept in shared memory)",
                    "dict": "cheb_step_ell<DICT> (block-dictionary matrix)",
                    "dict_diag": "cheb_step_ell<DICT,DIAG> (block-dictionary matrix, real-diagonal hopping blocks by DFMA)",

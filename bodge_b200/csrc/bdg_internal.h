@@ -99,6 +99,8 @@ struct ChebState {
     DevBuf vec[4];
     int cur = 0, prev = 1;
     bool pair = false;         // two steps per launch whenever two or more remain (cheb_pair.cu)
+    bool t2 = false;           // even-vector recursion E_{j+1} = 2 T_2(H~) E_j - E_{j-1}: vec[cur] = T_n, vec[prev] = T_{n-2}
+    int t2_rows_normalized = 0;  // launches whose dot rows have been rewritten in the single-step format
     int pair_grid_x = 0;
     PairWalk pair_walk;
     // dots[(step * 2 + which) * n_panels * PW + panel * PW + c]; which 0 = <T_n,T_n>, 1 = <T_{n+1},T_n>
@@ -174,6 +176,7 @@ int ensure_scratch(bdg_system *sys, int which, size_t bytes);
 // cheb.cu
 void cheb_release(bdg_system *sys);     // free all Chebyshev buffers
 void cheb_deactivate(bdg_system *sys);  // matrix changed: recursion state is stale, keep buffers
+int t2_finish_dots(bdg_system *sys);    // T2 mode: dot rows -> single-step format (call before reading st.dots)
 
 // cheb_ell.cu
 int ell_build(bdg_system *sys);                    // (re)build sys->ell from sys->packed when stale
@@ -185,5 +188,6 @@ void ell_release(bdg_system *sys);
 int pair_probe(bdg_system *sys);      // sets sys->ell.pair_usable / pair_M (called by ell_build)
 int pair_configure(bdg_system *sys);  // patch / segment plan and grid for the current ChebState
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step);
+int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

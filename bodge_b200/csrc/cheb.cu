@@ -327,6 +327,35 @@ __global__ void init_probes(double2 *__restrict__ x, int n_sites, int pw, int n_
     x[(((size_t)panel * n_sites + site) * pw + cl) * 4 + alpha] = make_double2(1.0, 0.0);
 }
 
+// T2 mode: the launches leave rows (a_j, c_j, b_j, d_j) = (<E_j,E_j>, <u_j,E_j>, <E_{j+1},E_j>, <E_{j+1},u_j>) with
+// E_j = T_2j x, u_j = H~ E_j.  From T_m T_n = (T_{m+n} + T_|m-n|) / 2:
+//     a_j = (mu_4j + mu_0)/2,                      b_j = (mu_{4j+2} + mu_2)/2,
+//     c_j = (mu_{4j+1} + mu_{4j-1})/4 + mu_1/2,    d_j = (mu_{4j+3} + mu_{4j+1})/4 + (mu_3 + mu_1)/4.
+// This rewrites the rows as the single-step kernels would have left them, D_n = (mu_n + mu_{n mod 2})/2, so that
+// every consumer (moments_from_dots, observables.cu) reads one format.  One thread per column; the odd moments
+// are a two-term recurrence along j (error grows like sqrt(j) eps mu_0).
+__global__ void __launch_bounds__(kThreads)
+t2_normalize(double *__restrict__ dots, int stride, int j_begin, int j_end) {
+    const int c = blockIdx.x * kThreads + threadIdx.x;
+    if (c >= stride) return;
+    auto row = [&](int n) -> double & { return dots[(size_t)n * stride + c]; };
+    if (j_begin == 0) {  // mu_0 = a_0, mu_1 = c_0, mu_2 = b_0, (mu_3 + mu_1)/2 = d_0
+        row(2) = 0.5 * (row(2) + row(0));
+        j_begin = 1;
+    }
+    const double mu0 = row(0), mu1 = row(1), mu2 = 2.0 * row(2) - mu0, mu3 = 2.0 * row(3) - mu1;
+    double odd = 2.0 * row(4 * j_begin - 1) - mu1;  // mu_{4j-1}
+    for (int j = j_begin; j < j_end; ++j) {
+        const double cj = row(4 * j + 1), bj = row(4 * j + 2), dj = row(4 * j + 3);
+        const double m1 = 4.0 * cj - 2.0 * mu1 - odd;         // mu_{4j+1}
+        const double m3 = 4.0 * dj - (mu3 + mu1) - m1;        // mu_{4j+3}
+        row(4 * j + 1) = 0.5 * (m1 + mu1);
+        row(4 * j + 2) = bj - 0.5 * mu2 + 0.5 * mu0;
+        row(4 * j + 3) = 0.5 * (m3 + mu1);
+        odd = m3;
+    }
+}
+
 // mu[n][c] from the per-step dot products: step s gave d0 = <T_s,T_s> (s = 0: <T_0,T_0>) and
 // d1 = <T_{s+1},T_s>;  mu_{2s} = 2 d0 - mu_0, mu_{2s+1} = 2 d1 - mu_1 for s >= 1.
 __global__ void __launch_bounds__(kThreads)
@@ -449,6 +478,21 @@ int ensure_dot_capacity(bdg_system *sys, int steps_total) {
 
 }  // namespace
 
+// T2 mode: bring the dot rows written since the last call into the single-step format (t2_normalize).
+int t2_finish_dots(bdg_system *sys) {
+    ChebState &st = sys->cheb;
+    if (!st.t2 || !st.active) return BDG_OK;
+    const int launches = (st.steps_done + 1) / 2;  // rows = 2 (steps_done + 1) = 4 per launch
+    if (st.t2_rows_normalized >= launches) return BDG_OK;
+    const int stride = st.n_panels * st.panel_width;
+    t2_normalize<<<(unsigned)ceil_div(stride, kThreads), kThreads, 0, sys->stream>>>(st.dots.as<double>(), stride,
+                                                                                     st.t2_rows_normalized, launches);
+    BDG_CUDA(cudaGetLastError());
+    st.t2_rows_normalized = launches;
+    st.launches += 1;
+    return BDG_OK;
+}
+
 void cheb_deactivate(bdg_system *sys) {
     sys->cheb.active = false;
     sys->ell.valid = false;
@@ -480,20 +524,24 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(n_cols >= 1, "need at least one column");
     BDG_REQUIRE(scale > 0.0, "scale must be positive");
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
-    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_PAIR, "unknown kernel %d", kernel);
+    BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_AUTO_MOMENTS, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
-    bool pair = false;
+    bool pair = false, t2 = false;
     if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT || kernel == BDG_KERNEL_DICT_DIAG ||
-        kernel == BDG_KERNEL_PAIR) {
+        kernel == BDG_KERNEL_PAIR || kernel == BDG_KERNEL_T2 || kernel == BDG_KERNEL_AUTO_MOMENTS) {
         BDG_TRY(ell_build(sys));
         // The pair kernel works on 8-column panels of the dictionary format; single leftover steps
         // (and T_1) run on the single-step dictionary kernel of the same format.
         const bool pair_ok = sys->ell.pair_usable && n_cols >= 5;
-        BDG_REQUIRE(kernel != BDG_KERNEL_PAIR || pair_ok,
-                    "the two-steps-per-pass kernel needs >= 5 columns and a block dictionary on a lattice with "
+        BDG_REQUIRE((kernel != BDG_KERNEL_PAIR && kernel != BDG_KERNEL_T2) || pair_ok,
+                    "the two-steps-per-pass kernels need >= 5 columns and a block dictionary on a lattice with "
                     "one-dimensional x-planes and an open nearest-neighbour stencil");
-        pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && pair_ok && sys->ell.diag_usable && auto_pair_enabled());
-        if (kernel == BDG_KERNEL_PAIR) kernel = BDG_KERNEL_AUTO;
+        const bool prefer = pair_ok && sys->ell.diag_usable && auto_pair_enabled();
+        // Callers that only read moments / observables get the even-vector recursion (three vector passes per
+        // two steps); callers that step and look at T_n, T_{n-1} the pair kernel (four).
+        t2 = kernel == BDG_KERNEL_T2 || (kernel == BDG_KERNEL_AUTO_MOMENTS && prefer);
+        pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && prefer);
+        if (kernel == BDG_KERNEL_PAIR || kernel == BDG_KERNEL_T2 || kernel == BDG_KERNEL_AUTO_MOMENTS) kernel = BDG_KERNEL_AUTO;
         BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
                     "the fixed-width (ELL) kernel needs block rows of <= 8 blocks with little padding");
         BDG_REQUIRE(kernel != BDG_KERNEL_DICT || sys->ell.dict_usable,
@@ -524,6 +572,8 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     st.cur = 0;
     st.prev = 1;
     st.pair = pair;
+    st.t2 = t2;
+    st.t2_rows_normalized = 0;
     st.dot_capacity = (int)(st.dots.bytes / ((size_t)2 * st.n_panels * st.panel_width * sizeof(double)));
 
     // Grid: enough CTAs to fill every SM at the kernel's occupancy, split over panels; each CTA
@@ -544,12 +594,12 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     }
 
     st.pair_grid_x = 0;
-    if (st.pair) BDG_TRY(pair_configure(sys));
+    if (st.pair || st.t2) BDG_TRY(pair_configure(sys));
 
     const size_t vec_elems = (size_t)st.n_panels * n * st.panel_width * 4;
     for (int b = 0; b < (st.pair ? 4 : 2); ++b) BDG_TRY(dev_alloc(sys, st.vec[b], vec_elems * sizeof(double2)));
     BDG_TRY(dev_alloc(sys, st.partials,
-                      (size_t)st.n_panels * std::max(st.grid_x, st.pair_grid_x) * (st.pair ? 32 : 16) * sizeof(double)));
+                      (size_t)st.n_panels * std::max(st.grid_x, st.pair_grid_x) * (st.pair || st.t2 ? 32 : 16) * sizeof(double)));
     BDG_TRY(dev_alloc(sys, st.tickets, (size_t)st.n_panels * sizeof(unsigned)));
     BDG_CUDA(cudaMemsetAsync(st.tickets.ptr, 0, (size_t)st.n_panels * sizeof(unsigned), sys->stream));
     BDG_TRY(ensure_dot_capacity(sys, 1024));
@@ -569,6 +619,16 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     }
     BDG_CUDA(cudaGetLastError());
     st.launches += 1;
+    if (st.t2) {
+        // E_1 = T_2(H~) E_0 into vec[1] and the dot products of steps 0 and 1 (moments 0..3): one step done.
+        BDG_TRY(ensure_dot_capacity(sys, 2));
+        BDG_TRY(t2_launch(sys, true, st.vec[0].ptr, st.vec[1].ptr, st.dots.as<double>()));
+        st.cur = 1;
+        st.prev = 0;
+        st.steps_done = 1;
+        st.launches += 1;
+        return BDG_OK;
+    }
     // T_1 = H~ T_0 (written into vec[1]); afterwards cur = 1 holds T_1, vec[0] holds T_0.
     BDG_TRY(launch_step(sys, true));
     return BDG_OK;
@@ -579,7 +639,7 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
     ChebState &st = sys->cheb;
     BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
     BDG_REQUIRE(n_steps >= 0, "negative step count");
-    BDG_TRY(ensure_dot_capacity(sys, st.steps_done + n_steps));
+    BDG_TRY(ensure_dot_capacity(sys, st.steps_done + n_steps + 1));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (elapsed_ms) {
         BDG_CUDA(cudaEventCreate(&e0));
@@ -588,7 +648,16 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
         BDG_CUDA(cudaEventRecord(e0, sys->stream));
     }
     for (int s = 0; s < n_steps;) {
-        if (st.pair && n_steps - s >= 2) {
+        if (st.t2) {  // two steps per launch, always: an odd request is rounded up (moments-only mode)
+            const int stride = st.n_panels * st.panel_width;
+            BDG_TRY(ensure_dot_capacity(sys, st.steps_done + 2));
+            BDG_TRY(t2_launch(sys, false, st.vec[st.cur].ptr, st.vec[st.prev].ptr,
+                              st.dots.as<double>() + (size_t)(st.steps_done + 1) * 2 * stride));
+            std::swap(st.cur, st.prev);
+            st.launches += 1;
+            st.steps_done += 2;
+            s += 2;
+        } else if (st.pair && n_steps - s >= 2) {
             BDG_TRY(launch_pair(sys));
             st.steps_done += 2;
             s += 2;
@@ -629,6 +698,7 @@ extern "C" int bdg_cheb_moments_read(bdg_t *sys, int32_t n_moments, int reduce, 
     BDG_REQUIRE(n_moments >= 1 && n_moments <= 2 * (st.steps_done + 1), "only %d moments available, %d requested",
                 2 * (st.steps_done + 1), n_moments);
     BDG_REQUIRE(reduce == BDG_MU_PER_COLUMN || reduce == BDG_MU_SUM, "unknown reduce mode");
+    BDG_TRY(t2_finish_dots(sys));
     const int n_out = reduce ? 1 : st.n_cols;
     const size_t count = (size_t)n_moments * n_out;
     double *dst = mu;
@@ -651,8 +721,8 @@ extern "C" int bdg_cheb_moments(bdg_t *sys, int kind, int32_t n_cols, const int6
                                 int64_t col_offset, double scale, int32_t n_moments, int reduce, double *mu,
                                 int mu_on_device) {
     BDG_REQUIRE(n_moments >= 1, "need at least one moment");
-    BDG_TRY(bdg_cheb_begin(sys, kind, n_cols, probe_rows, seed, col_offset, scale, BDG_KERNEL_AUTO));
-    BDG_TRY(bdg_cheb_steps(sys, (n_moments + 1) / 2 - 1, nullptr));
+    BDG_TRY(bdg_cheb_begin(sys, kind, n_cols, probe_rows, seed, col_offset, scale, BDG_KERNEL_AUTO_MOMENTS));
+    BDG_TRY(bdg_cheb_steps(sys, std::max(0, (n_moments + 1) / 2 - 1 - sys->cheb.steps_done), nullptr));
     return bdg_cheb_moments_read(sys, n_moments, reduce, mu, mu_on_device);
 }
 
@@ -661,6 +731,7 @@ extern "C" int bdg_cheb_vectors(bdg_t *sys, int which, double *out) {
     ChebState &st = sys->cheb;
     BDG_REQUIRE(st.active && out, "no active recursion or null output");
     BDG_REQUIRE(which == 0 || which == 1, "which must be 0 (T_n) or 1 (T_{n-1})");
+    BDG_REQUIRE(which == 0 || !st.t2, "the even-vector recursion (kernel T2) keeps T_n and T_{n-2}, not T_{n-1}");
     const BsrDev &m = sys->packed;
     const size_t count = (size_t)m.n_sites * 4 * st.n_cols;
     DevBuf tmp;
@@ -695,10 +766,10 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
     const BsrDev &m = sys->packed;
     const EllDev &e = sys->ell;
-    if (kernel) *kernel = st.pair ? BDG_KERNEL_PAIR : st.kernel;
+    if (kernel) *kernel = st.t2 ? BDG_KERNEL_T2 : st.pair ? BDG_KERNEL_PAIR : st.kernel;
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
-        if (st.pair)  // one pass over the codes and indices serves two steps
+        if (st.pair || st.t2)  // one pass over the codes and indices serves two steps
             *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;

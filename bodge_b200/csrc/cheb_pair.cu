@@ -82,6 +82,12 @@ __device__ __forceinline__ double2 ld_prev(const double2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// ... and E_{j-1} of the T2 mode, which the same thread overwrites one iteration later (no .nc)
+__device__ __forceinline__ double2 ld_prev_rw(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void ld_table_pred(double &v, const double *p, unsigned take) {
     asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(v) : "l"(p), "r"(take));
 }
@@ -160,12 +166,20 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
 // all the same and meets a zero fragment: the rings are cleared once, so whatever sits there is an
 // earlier, finite, vector value.  Warps whose site does not exist (ragged last patch) compute on
 // whatever the rings hold and store nothing: the row body has no branches.
-template <bool DIAG, int NW, int S, int MINB>
+//
+// MODE 1 ("T2", the doubled-argument recursion) runs the same two sub-steps on the EVEN vectors only:
+//     E_j = T_2j(H~) x,   E_{j+1} = 2 T_2(H~) E_j - E_{j-1} = 4 H~ (H~ E_j) - 2 E_j - E_{j-1}
+// [A] u = H~ E_j (halo included, shared memory only, never stored), [B] E_{j+1} for the owned rows, written in
+// place over E_{j-1} (read by its owner alone).  One launch is still two applications of H~ and four dot products
+//     a = <E_j, E_j>, c = <u, E_j>, b = <E_{j+1}, E_j>, d = <E_{j+1}, u>
+// from which the same four moments follow (cheb.cu: t2_normalize), but it moves THREE vector passes instead
+// of four, and two vector buffers suffice.  `first`: E_1 = T_2(H~) E_0 = 2 H~ u - E_0 (E_{-1} = E_1).
+template <bool DIAG, int NW, int S, int MINB, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
                double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
-               double alpha, double *__restrict__ partials, unsigned *__restrict__ tickets,
+               double alpha, double alpha2, int first, double *__restrict__ partials, unsigned *__restrict__ tickets,
                double *__restrict__ dots_step, const PairWalk wk) {
     constexpr int W = NW * S, R = kRecBytes;
     constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
@@ -178,7 +192,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const int panel = blockIdx.y;
     const size_t pbase = (size_t)panel * n_sites * 32;
     const double2 *ta = xa + pbase, *tb = xb + pbase;
-    double2 *tc = xc + pbase, *td = xd + pbase;
+    double2 *tc = xc + pbase, *td = xd + pbase;  // MODE 1: td = ta (E_{j+1} over E_{j-1}), tc unused
     const int l0 = S * warp;  // this warp's sites: l0, l0 + 1
     // own-record addresses of site l0 in slot 0 of each ring (+ lane's 16 bytes)
     uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
@@ -254,7 +268,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             pvn[s] = make_double2(0.0, 0.0);
-            if (prev_ok[s]) pvn[s] = ld_prev(ta + gout + 32 * s);
+            if (MODE == 0 && prev_ok[s]) pvn[s] = ld_prev(ta + gout + 32 * s);
         }
         for (int q = tlo; q <= xlo; ++q) wait(q);
 
@@ -265,7 +279,11 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 pv[s] = pvn[s];
-                if (x + 1 < xhi && prev_ok[s]) pvn[s] = ld_prev(ta + gout + gstep + 32 * s);
+                if (MODE == 0) {
+                    if (x + 1 < xhi && prev_ok[s]) pvn[s] = ld_prev(ta + gout + gstep + 32 * s);
+                } else {  // E_{j-1}(x, y) for [B](x) of the next iteration; this thread overwrites it there
+                    if (x >= x0 && x < x1 && owned[s] && !first) pvn[s] = ld_prev_rw(ta + gout + 32 * s);
+                }
             }
             wait(x + 1);
             const bool do_a = x < xhi;
@@ -289,13 +307,14 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
                     row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
-                    out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
+                    if (MODE == 0) out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
+                    else out[s] = make_double2(alpha * yr, alpha * yi);
                     sts_rec(t1 + (uint32_t)s * R, out[s]);
                 }
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     if (store && owned[s]) {
-                        tc[gout + 32 * s] = out[s];
+                        if (MODE == 0) tc[gout + 32 * s] = out[s];
                         d0 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
                         d1 += out[s].x * c[1 + s].x + out[s].y * c[1 + s].y;
                     }
@@ -323,10 +342,20 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
                     row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
-                    const double2 out = make_double2(fma(alpha, yr, -tn[s].x), fma(alpha, yi, -tn[s].y));
+                    double2 out;
+                    if (MODE == 0) {
+                        out = make_double2(fma(alpha, yr, -tn[s].x), fma(alpha, yi, -tn[s].y));
+                    } else {
+                        const double2 sub = first ? tn[s] : make_double2(fma(2.0, tn[s].x, pv[s].x), fma(2.0, tn[s].y, pv[s].y));
+                        out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
+                    }
                     if (owned[s]) {
                         td[gout - gstep + 32 * s] = out;
-                        d2 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
+                        if (MODE == 0) {
+                            d2 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
+                        } else {
+                            d2 += out.x * tn[s].x + out.y * tn[s].y;
+                        }
                         d3 += out.x * c[1 + s].x + out.y * c[1 + s].y;
                     }
                 }
@@ -417,10 +446,11 @@ pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, cons
 }
 
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
-                            double2 *, int, int, double, double *, unsigned *, double *, const PairWalk);
+                            double2 *, int, int, double, double, int, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag) {
-    return diag ? cheb_pair_step<true, NW, S, MINB> : cheb_pair_step<false, NW, S, MINB>;
+template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag, bool t2) {
+    if (t2) return diag ? cheb_pair_step<true, NW, S, MINB, 1> : cheb_pair_step<false, NW, S, MINB, 1>;
+    return diag ? cheb_pair_step<true, NW, S, MINB, 0> : cheb_pair_step<false, NW, S, MINB, 0>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -434,15 +464,15 @@ struct PairShape {
     size_t smem;
 };
 
-PairShape pair_shape(bool diag) {
+PairShape pair_shape(bool diag, bool t2) {
     PairShape s;
     // 8 warps x 2 sites: two CTAs per SM, one computes while the other waits at its barrier.  The shape
     // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
     // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
     if (env_int("BDG_PAIR_WARPS", 8) <= 8)
-        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag);
+        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, t2);
     else
-        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag);
+        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, t2);
     const int W = s.warps * s.sites;
     s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * kRingN;
     return s;
@@ -485,7 +515,7 @@ int pair_probe(bdg_system *sys) {
 int pair_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, st.t2);
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
@@ -521,17 +551,32 @@ int pair_configure(bdg_system *sys) {
     return BDG_OK;
 }
 
-// T_{n+1} -> x_next1, T_{n+2} -> x_next2 and the dot products of both steps (dots_step: 4 rows).
+// Pair mode: T_{n+1} -> x_next1, T_{n+2} -> x_next2 and the dot products of both steps (dots_step: 4 rows).
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const bool diag = st.kernel == BDG_KERNEL_DICT_DIAG;
-    const PairShape shape = pair_shape(diag);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, false);
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
-        e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev), static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1),
-        static_cast<double2 *>(x_next2), (int)e.n_sites, st.n_panels, 2.0 / st.scale, st.partials.as<double>(),
-        st.tickets.as<unsigned>(), dots_step, st.pair_walk);
+        e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev),
+        static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1), static_cast<double2 *>(x_next2),
+        (int)e.n_sites, st.n_panels, 2.0 / st.scale, 0.0, 0, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step,
+        st.pair_walk);
+    BDG_CUDA(cudaGetLastError());
+    return BDG_OK;
+}
+
+// T2 mode: E_{j+1} = 2 T_2(H~) E_j - E_{j-1} written over E_{j-1} (x_io); first: E_1 = T_2(H~) E_0.
+int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step) {
+    ChebState &st = sys->cheb;
+    const EllDev &e = sys->ell;
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, true);
+    dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
+    shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
+        e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_io),
+        static_cast<const double2 *>(x_cur), nullptr, static_cast<double2 *>(x_io), (int)e.n_sites, st.n_panels,
+        1.0 / st.scale, (first ? 2.0 : 4.0) / st.scale, first ? 1 : 0, st.partials.as<double>(), st.tickets.as<unsigned>(),
+        dots_step, st.pair_walk);
     BDG_CUDA(cudaGetLastError());
     return BDG_OK;
 }

@@ -74,7 +74,7 @@ static int check_active(bdg_system *sys, int32_t n_moments) {
     BDG_REQUIRE(st.active, "bdg_cheb_begin has not been called");
     BDG_REQUIRE(n_moments >= 1 && n_moments <= 2 * (st.steps_done + 1), "only %d moments available, %d requested",
                 2 * (st.steps_done + 1), n_moments);
-    return BDG_OK;
+    return t2_finish_dots(sys);  // (the even-vector recursion leaves its dot rows in another form)
 }
 
 extern "C" int bdg_kpm_resolvent(bdg_t *sys, int32_t n_moments, int32_t n_z, const double *w, const double *pref,

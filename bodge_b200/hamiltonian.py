@@ -250,6 +250,8 @@ class Hamiltonian:
         if batch is None:  # two vector sets of 64*N*k bytes each (four with the pair kernel); keep two under ~16 GB
             batch = max(8, int(8e9 // (64 * self.lattice.size)) // 8 * 8)
         steps = (moments + 1) // 2 - 1
+        if kernel == "auto":   # only moments are read here: the library may keep every second vector only
+            kernel = "auto_moments"
         parts = []
         for b0 in range(0, n_local, batch):
             b1 = min(n_local, b0 + batch)
@@ -257,7 +259,8 @@ class Hamiltonian:
                 self._sys.cheb_begin(probe_rows=rows[lo + b0 : lo + b1], scale=scale, kernel=kernel)
             else:
                 self._sys.cheb_begin(n_random=b1 - b0, seed=seed, col_offset=lo + b0, scale=scale, kernel=kernel)
-            self._sys.cheb_steps(steps)
+            done = self._sys.cheb_available() // 2 - 1      # steps bdg_cheb_begin has already taken (1 with T2)
+            self._sys.cheb_steps(max(0, steps - done))
             parts.append(np.asarray(read(self._sys, b1 - b0), dtype=np.float64))
         if summed:
             local = np.sum(parts, axis=0) if parts else None

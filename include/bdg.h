@@ -117,6 +117,15 @@ enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
 /* AUTO = PAIR where its DFMA variant applies (DICT_DIAG matrix, open 2-D stencil, >= 5 columns), else DICT_DIAG,
  *        else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+ * AUTO_MOMENTS = AUTO for callers that only read moments / observables (never T_{n-1}): T2 where PAIR would be
+ *        chosen, else as AUTO.  bdg_cheb_moments and the Python observables use it;
+ * T2   = the even-vector ("doubled argument") recursion E_{j+1} = 2 T_2(H~) E_j - E_{j-1}, E_j = T_2j(H~) x, on the
+ *        PAIR kernel: two applications of H~ per launch like PAIR, but only T_n and T_{n-2} are kept, so a launch
+ *        moves three vector passes instead of four and two buffers suffice.  The four dot products of a launch
+ *        (<E_j,E_j>, <H~E_j,E_j>, <E_{j+1},E_j>, <E_{j+1},H~E_j>) give the same four moments through
+ *        T_m T_n = (T_{m+n} + T_|m-n|)/2 (odd ones by a two-term recurrence).  Steps advance in twos (an odd
+ *        bdg_cheb_steps request is rounded up), bdg_cheb_begin already performs the first (T_2), and
+ *        bdg_cheb_vectors(which = 1) is not available.  Same requirements as PAIR;
  * PAIR = two recursion steps per launch on the DICT / DICT_DIAG format: T_{n+1} is consumed out of shared
  *        memory instead of coming back from HBM, so two steps move four vector passes instead of six.  Needs
  *        >= 5 columns and a lattice with one-dimensional x-planes (Lz = 1 or Ly = 1) whose stored blocks form
@@ -137,7 +146,7 @@ enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
  *        per-CTA-chunk row traversal (tuning references). */
 enum { BDG_KERNEL_AUTO = 0, BDG_KERNEL_DMMA = 1, BDG_KERNEL_FMA = 2, BDG_KERNEL_ELL = 3,
        BDG_KERNEL_DMMA_SIMPLE = 4, BDG_KERNEL_DMMA_CHUNKED = 5, BDG_KERNEL_DICT = 6, BDG_KERNEL_DICT_DIAG = 7,
-       BDG_KERNEL_PAIR = 8 };
+       BDG_KERNEL_PAIR = 8, BDG_KERNEL_T2 = 9, BDG_KERNEL_AUTO_MOMENTS = 10 };
 
 /* Start a recursion on n_cols start vectors resident on this GPU.
  *   kind = BDG_X0_PROBE:      column c = unit vector e_{probe_rows[c]}           (LDOS-type)

@@ -32,7 +32,7 @@ for item in sys.argv[1:]:
         ms = s.cheb_steps(steps, timed=True)
         info, fmt = s.cheb_info(), s.cheb_format()
         gbs = info["bytes_per_step"] * steps / (ms * 1e-3) / 1e9
-        passes = 128 if fmt["kernel"] == "pair" else 192   # pair: 4 vector passes per 2 steps
+        passes = {"pair": 128, "t2": 96}.get(fmt["kernel"], 192)   # pair: 4 vector passes per 2 steps, t2: 3
         actual = (fmt["matrix_bytes_per_step"] + passes * system.lattice.size * int(k)) * steps / (ms * 1e-3) / 1e9
         print(json.dumps(dict(cfg=cfg, k=int(k), kernel=fmt["kernel"], np=os.environ.get("BDG_ELL_NP"), ms_per_step=round(ms / steps, 5),
                               steps_per_s=round(steps / (ms * 1e-3), 1), alg_GBps=round(gbs), frac=round(gbs / PEAK, 4),

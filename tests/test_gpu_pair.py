@@ -160,6 +160,89 @@ def test_pair_follows_matrix_updates(gpu_api):
     assert rel_err(after, orc.cheb_moments(Hm, orc.rademacher(2, Hm.shape[0], np.arange(8)), 32, scale)) <= TOL
 
 
+# ---- the even-vector recursion (kernel="t2"): same kernel, E_{j+1} = 2 T_2(H~) E_j - E_{j-1} -------------------
+@pytest.mark.parametrize("tag", sorted(SYSTEMS))
+def test_t2_moments_match_the_oracle(gpu_api, monkeypatch, tag):
+    """Three vector passes per two steps: only T_2j are kept, the four dot products of a launch give the same four
+    moments (odd ones through a two-term recurrence).  Another rounding sequence than the three-term recursion,
+    so: 1e-10 against the oracle (BASELINE.json), 1e-12 against the pair kernel, bit-reproducible."""
+    build, diag = SYSTEMS[tag]
+    system = build(gpu_api)
+    H = system.matrix("bsr")
+    scale = system.spectral_bound()
+    for plan in PLANS[:4]:
+        _set_plan(monkeypatch, plan)
+        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2), (8, 5), (6, 1), (8, 301)):
+            got = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="t2")
+            assert system._sys.cheb_format()["kernel"] == "t2"
+            want = orc.cheb_moments(H, orc.rademacher(3, H.shape[0], np.arange(n_cols)), n_moments, scale)
+            assert got.shape == want.shape
+            assert rel_err(got, want) <= TOL
+            pair = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="pair")
+            assert rel_err(got, pair) <= 1e-12
+            assert np.array_equal(got, system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="t2"))
+    summed = system.chebyshev_moments(48, vectors=8, seed=3, scale=scale, kernel="t2", summed=True)
+    assert rel_err(summed, system.chebyshev_moments(48, vectors=8, seed=3, scale=scale, kernel="t2").sum(axis=1)) <= 1e-13
+
+
+def test_t2_vectors_steps_and_incremental_reads(gpu_api):
+    """bdg_cheb_begin takes the first step (T_2), bdg_cheb_steps advances in twos, T_n agrees with the three-term
+    recursion to rounding, T_{n-1} is not kept; moments can be read between calls (the dot rows are brought
+    into the single-step format incrementally)."""
+    system = cases.junction(gpu_api, (30, 40, 1))
+    sysn = system._sys
+    scale = system.spectral_bound()
+    sysn.cheb_begin(n_random=8, seed=5, col_offset=3, scale=scale, kernel="t2")
+    assert sysn.cheb_available() == 4
+    first = sysn.cheb_read(4, 8)
+    sysn.cheb_steps(6)                       # three launches: T_8
+    assert sysn.cheb_available() == 16
+    mid = sysn.cheb_read(16, 8)
+    sysn.cheb_steps(3)                       # rounded up to four steps: T_12
+    assert sysn.cheb_available() == 24
+    last = sysn.cheb_read(24, 8)
+    t12 = sysn.cheb_vectors(8, 0)
+    with pytest.raises(ValueError):
+        sysn.cheb_vectors(8, 1)
+    sysn.cheb_begin(n_random=8, seed=5, col_offset=3, scale=scale, kernel="dict_diag")
+    sysn.cheb_steps(11)                      # T_12 by the three-term recursion
+    want = sysn.cheb_vectors(8, 0)
+    ref = sysn.cheb_read(24, 8)
+    sysn.cheb_end()
+    assert np.max(np.abs(t12 - want)) <= 1e-13 * np.max(np.abs(want))
+    assert rel_err(last, ref) <= 1e-12
+    assert np.array_equal(first, last[:4]) and np.array_equal(mid, last[:16])
+
+
+def test_t2_observables_and_auto_moments(gpu_api):
+    """chebyshev_moments / ldos_map / free_energy only read moments: their kernel="auto" is the even-vector
+    recursion wherever kernel="auto" of the stepping API is the pair kernel."""
+    system = cases.junction(gpu_api, (30, 40, 1))
+    H = system.matrix("bsr")
+    scale = system.spectral_bound()
+    rows = [4 * system.lattice.index((x, y, 0)) + a for (x, y) in ((0, 0), (29, 39), (14, 29), (15, 30)) for a in (0, 3)]
+    got = system.chebyshev_moments(64, rows=rows, scale=scale)
+    assert system._sys.cheb_format()["kernel"] == "t2"
+    x0 = np.zeros((H.shape[0], len(rows)), dtype=np.complex128)
+    x0[rows, np.arange(len(rows))] = 1.0
+    assert rel_err(got, orc.cheb_moments(H, x0, 64, scale)) <= TOL
+    E = np.linspace(-0.3, 0.3, 9)
+    sites = [(14, 29, 0), (0, 39, 0)]
+    assert rel_err(system.ldos_map(sites, E), system.ldos_map(sites, E, kernel="dict_diag")) <= 1e-10
+    assert system._sys.cheb_format()["kernel"] == "dict_diag"
+    F = system.free_energy(0.1, cuda=True, vectors=16, moments=512)
+    assert system._sys.cheb_format()["kernel"] == "t2"
+    assert abs(F - system.free_energy(0.1, cuda=True, vectors=16, moments=512, kernel="dict_diag")) <= 1e-10 * abs(F)
+    # where the pair kernel is not the stepping default, auto_moments is plain auto
+    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
+        other.chebyshev_moments(16, vectors=8, seed=1)
+        assert other._sys.cheb_format()["kernel"] == want
+    system.chebyshev_moments(16, vectors=4, seed=1)
+    assert system._sys.cheb_format()["kernel"] == "dict_diag"
+    with pytest.raises(ValueError):
+        cases.swave_3d(gpu_api, (6, 5, 4))._sys.cheb_begin(n_random=8, seed=1, scale=10.0, kernel="t2")
+
+
 def test_pair_full_size_junction():
     """C5 (10^6 sites, 8 columns): vectors after 2 x 3 + 1 steps bit-identical to the single-step kernel,
     moments to rounding, mu_0 = 4N exactly, bit-reproducible."""
@@ -180,3 +263,8 @@ def test_pair_full_size_junction():
     assert rel_err(pair, single) <= 1e-13
     assert np.array_equal(pair[0], np.full(8, float(system.shape[0])))
     assert np.array_equal(pair, system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale, kernel="pair"))
+    t2 = system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale, kernel="t2")
+    assert rel_err(t2, single) <= 1e-12
+    assert np.array_equal(t2[0], np.full(8, float(system.shape[0])))
+    assert np.array_equal(t2, system.chebyshev_moments(40, vectors=8, seed=1234, scale=scale))   # the observables' default
+    assert system._sys.cheb_format()["kernel"] == "t2"
