@@ -378,7 +378,8 @@ def run_ours(args):
     # (the even-vector recursion "t2" moves three per two steps)
     moved_step = fmt["matrix_bytes_per_step"] + {"pair": 128, "t2": 96}.get(fmt["kernel"], 192) * n_sites * cols
     moved = moved_step * K / (kernel_ms * 1e-3) / 1e9
-    step_launches = max(launches - 1, 1)   # `launches` also counts the moment read-out kernel
+    # `launches` also counts the moment read-out kernel (and, for t2, the kernel that normalises its dot rows)
+    step_launches = max(launches - (2 if fmt["kernel"] == "t2" else 1), 1)
     steps_per_launch = K / step_launches
     kernel_name = {"t2": "cheb_pair_step<MODE=T2> (two applications of H~ per launch on the even vectors E_j = T_2j x: "
                          "E_{j+1} = 2 T_2(H~) E_j - E_{j-1}; block-dictionary matrix, E_j planes staged in shared memory by TMA "
