@@ -185,6 +185,22 @@ def test_t2_moments_match_the_oracle(gpu_api, monkeypatch, tag):
     assert rel_err(summed, system.chebyshev_moments(48, vectors=8, seed=3, scale=scale, kernel="t2").sum(axis=1)) <= 1e-13
 
 
+def test_t2_long_recursion_stays_within_tolerance(gpu_api):
+    """4096 moments (2047 steps): the odd moments of the even-vector recursion come from a two-term recurrence along
+    the launches, whose rounding error grows like sqrt(j) eps mu_0 -- far inside the 1e-10 of BASELINE.json."""
+    system = cases.readme_swave(gpu_api, (24, 16, 1))
+    H = system.matrix("bsr")
+    scale = system.spectral_bound()
+    got = system.chebyshev_moments(4096, vectors=8, seed=11, scale=scale, kernel="t2")
+    want = orc.cheb_moments(H, orc.rademacher(11, H.shape[0], np.arange(8)), 4096, scale)
+    assert rel_err(got, want) <= 1e-11
+    assert rel_err(got, system.chebyshev_moments(4096, vectors=8, seed=11, scale=scale, kernel="pair")) <= 1e-11
+    # ... and the observable built on them: exact-trace free energy against the dense spectrum
+    F = system.free_energy(0.1, cuda=True)
+    assert system._sys.cheb_format()["kernel"] == "t2"
+    assert abs(F - system.free_energy(0.1)) <= 1e-10 * abs(F)
+
+
 def test_t2_vectors_steps_and_incremental_reads(gpu_api):
     """bdg_cheb_begin takes the first step (T_2), bdg_cheb_steps advances in twos, T_n agrees with the three-term
     recursion to rounding, T_{n-1} is not kept; moments can be read between calls (the dot rows are brought
