@@ -330,6 +330,18 @@ def run_ours(args):
         plain = {"kernel": "cheb_step_ell (every block from HBM)", "kernel_ms_per_launch": p_kernel / K,
                  "steps_per_s": world * K / (p_total * 1e-3), "matrix_bytes_per_launch": p_fmt["matrix_bytes_per_step"]}
 
+    # The literal three-term recursion T_{n+1} = 2 H~ T_n - T_{n-1} (every T_n materialised) for comparison when the
+    # headline ran the even-vector form of it: the pair kernel (two steps per launch) and the single-step kernel.
+    three_term = None
+    if fmt["kernel"] == "t2" and not args.no_plain:
+        three_term = {}
+        for name in ("pair", "dict_diag"):
+            try:
+                t_total, t_kernel, t_launches, _, t_fmt = timed_steps(name)
+            except (ValueError, RuntimeError):
+                continue
+            three_term[t_fmt["kernel"]] = {"steps_per_s": world * K / (t_total * 1e-3), "kernel_ms_per_step": t_kernel / K}
+
     # ---- end to end through the public API with host buffers -------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -397,6 +409,8 @@ def run_ours(args):
                 "kernel_ms_per_launch": kernel_ms / step_launches, "matrix_format": fmt["kernel"],
                 "distinct_blocks": fmt["distinct_blocks"], "moved_bytes_per_launch": moved_step * steps_per_launch,
                 "moved_GBps": moved, "moved_frac": moved / peak}
+    if three_term:
+        roofline["three_term_recursion"] = three_term
     if plain is not None:
         plain["achieved"] = bytes_step / (plain["kernel_ms_per_launch"] * 1e-3) / 1e9
         plain["frac"] = plain["achieved"] / peak
@@ -420,7 +434,10 @@ def run_ours(args):
         "config": {"workload": cfg["label"], "config": args.config, "n_sites": n_sites, "n_blocks": info["n_blocks"],
                    "cols_per_gpu": cols, "parallelism": f"column shards x{world}, matrix replicated",
                    "l2": "inputs (1.3 GB matrix + 1.0 GB vectors) exceed the 126 MB L2; no flush needed",
-                   "kernel": fmt["kernel"], "panel_width": info["panel_width"]},
+                   "kernel": fmt["kernel"], "panel_width": info["panel_width"],
+                   "recursion": ("even-vector form E_{j+1} = 2 T_2(H~) E_j - E_{j-1}, E_j = T_2j(H~) x: one launch = two applications "
+                                 "of H~ = two steps = four moments (roofline.three_term_recursion: the literal recursion)"
+                                 if fmt["kernel"] == "t2" else "three-term T_{n+1} = 2 H~ T_n - T_{n-1}")},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "assembly": assembly,
     }
