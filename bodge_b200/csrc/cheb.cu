@@ -345,14 +345,28 @@ t2_normalize(double *__restrict__ dots, int stride, int j_begin, int j_end) {
     }
     const double mu0 = row(0), mu1 = row(1), mu2 = 2.0 * row(2) - mu0, mu3 = 2.0 * row(3) - mu1;
     double odd = 2.0 * row(4 * j_begin - 1) - mu1;  // mu_{4j-1}
-    for (int j = j_begin; j < j_end; ++j) {
-        const double cj = row(4 * j + 1), bj = row(4 * j + 2), dj = row(4 * j + 3);
-        const double m1 = 4.0 * cj - 2.0 * mu1 - odd;         // mu_{4j+1}
-        const double m3 = 4.0 * dj - (mu3 + mu1) - m1;        // mu_{4j+3}
-        row(4 * j + 1) = 0.5 * (m1 + mu1);
-        row(4 * j + 2) = bj - 0.5 * mu2 + 0.5 * mu0;
-        row(4 * j + 3) = 0.5 * (m3 + mu1);
-        odd = m3;
+    // Chunks of kChunk launches: all loads of a chunk are issued before its first store (the stores go to the
+    // same array, so the compiler cannot hoist later loads over them: one memory latency per chunk, not per j).
+    constexpr int kChunk = 8;
+    for (int j0 = j_begin; j0 < j_end; j0 += kChunk) {
+        double cj[kChunk], bj[kChunk], dj[kChunk];
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+            const int j = min(j0 + i, j_end - 1);
+            cj[i] = row(4 * j + 1), bj[i] = row(4 * j + 2), dj[i] = row(4 * j + 3);
+        }
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+            const int j = j0 + i;
+            if (j < j_end) {
+                const double m1 = 4.0 * cj[i] - 2.0 * mu1 - odd;   // mu_{4j+1}
+                const double m3 = 4.0 * dj[i] - (mu3 + mu1) - m1;  // mu_{4j+3}
+                row(4 * j + 1) = 0.5 * (m1 + mu1);
+                row(4 * j + 2) = bj[i] - 0.5 * mu2 + 0.5 * mu0;
+                row(4 * j + 3) = 0.5 * (m3 + mu1);
+                odd = m3;
+            }
+        }
     }
 }
 
