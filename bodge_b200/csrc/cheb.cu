@@ -546,10 +546,15 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
         BDG_TRY(ell_build(sys));
         // The pair kernel works on 8-column panels of the dictionary format; single leftover steps
         // (and T_1) run on the single-step dictionary kernel of the same format.
-        const bool pair_ok = sys->ell.pair_usable && n_cols >= 5;
+        // The two-step kernels work on 8-column panels.  Fewer than 5 columns (ldos() of one site = 4) are padded to
+        // a panel when the vectors are small enough to live in L2 (<= 64 Ki sites: 32 MB per vector): such runs are
+        // launch-latency-bound, and two steps per launch halve the launches; at HBM-bound sizes the padding would
+        // cost more bytes than the fusion saves, so narrow panels stay on the single-step kernels there.
+        const bool small = sys->ell.n_sites <= (1 << 16);
+        const bool pair_ok = sys->ell.pair_usable && (n_cols >= 5 || small);
         BDG_REQUIRE((kernel != BDG_KERNEL_PAIR && kernel != BDG_KERNEL_T2) || pair_ok,
-                    "the two-steps-per-pass kernels need >= 5 columns and a block dictionary on a lattice with "
-                    "one-dimensional x-planes and an open nearest-neighbour stencil");
+                    "the two-steps-per-pass kernels need >= 5 columns (any number on lattices of <= 65536 sites) and a block "
+                    "dictionary on a lattice with one-dimensional x-planes and an open nearest-neighbour stencil");
         const bool prefer = pair_ok && sys->ell.diag_usable && auto_pair_enabled();
         // Callers that only read moments / observables get the even-vector recursion (three vector passes per
         // two steps); callers that step and look at T_n, T_{n-1} the pair kernel (four).
@@ -579,7 +584,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     st.active = false;
     st.kernel = kernel;
     st.n_cols = n_cols;
-    st.panel_width = n_cols >= 5 ? 8 : (n_cols >= 3 ? 4 : n_cols);
+    st.panel_width = (n_cols >= 5 || pair || t2) ? 8 : (n_cols >= 3 ? 4 : n_cols);
     st.n_panels = (int)ceil_div(n_cols, st.panel_width);
     st.scale = scale;
     st.steps_done = 0;

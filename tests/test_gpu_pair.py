@@ -55,7 +55,8 @@ def test_pair_vectors_are_bit_identical_to_the_single_step_kernel(gpu_api, monke
     scale = system.spectral_bound()
     base = "dict_diag" if diag else "dict"
     _set_plan(monkeypatch, plan)
-    for n_cols, steps in ((8, 6), (5, 7), (19, 2), (12, 1)):   # odd counts end on a single step; 1 = no pair at all
+    # odd counts end on a single step; 1 = no pair at all; < 5 columns: padded to an 8-column panel (small lattices)
+    for n_cols, steps in ((8, 6), (5, 7), (19, 2), (12, 1), (4, 6), (1, 5)):
         (cur, prev), fmt = _vectors(system._sys, "pair", n_cols, steps, scale)
         assert fmt == "pair"
         (want_cur, want_prev), fmt = _vectors(system._sys, base, n_cols, steps, scale)
@@ -72,7 +73,7 @@ def test_pair_moments_match_the_oracle(gpu_api, monkeypatch, tag):
     scale = system.spectral_bound()
     for plan in PLANS[:3]:
         _set_plan(monkeypatch, plan)
-        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2)):
+        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2), (4, 33), (2, 20)):
             got = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="pair")
             want = orc.cheb_moments(H, orc.rademacher(3, H.shape[0], np.arange(n_cols)), n_moments, scale)
             assert got.shape == want.shape
@@ -109,9 +110,19 @@ def test_pair_declines_what_it_cannot_do(gpu_api):
     periodic = cases.random_periodic(gpu_api, (3, 5, 7), seed=11)._sys   # no dictionary, wrap-around bonds
     with pytest.raises(ValueError):
         periodic.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    big = b.Hamiltonian(b.CubicLattice((260, 260, 1)))           # 67,600 sites: past the L2-resident size up to which
+    big.fill(*workloads.readme_swave((260, 260, 1)))             # narrow column sets are padded to an 8-column panel
+    with pytest.raises(ValueError):
+        big._sys.cheb_begin(n_random=4, seed=1, scale=scale, kernel="pair")
+    big._sys.cheb_begin(n_random=4, seed=1, scale=scale, kernel="auto")
+    assert big._sys.cheb_format()["kernel"] == "dict_diag"
+    big._sys.cheb_begin(n_random=5, seed=1, scale=scale, kernel="auto")
+    assert big._sys.cheb_format()["kernel"] == "pair"
+    del big
     flat = cases.readme_swave(gpu_api, (12, 12, 1))
-    with pytest.raises(ValueError):                              # panels of fewer than 8 columns
-        flat._sys.cheb_begin(n_random=4, seed=1, scale=scale, kernel="pair")
     # wrap-around hopping along y on an otherwise qualifying lattice
     lattice = flat.lattice
     with flat as (H, D):
@@ -127,11 +138,12 @@ def test_pair_declines_what_it_cannot_do(gpu_api):
 
 
 def test_auto_prefers_pair_where_it_is_faster(gpu_api, monkeypatch):
-    """kernel="auto": two steps per pass when the hopping blocks are real-diagonal (DFMA rows) and a panel
-    has 8 columns; single-step kernels otherwise; BDG_AUTO_PAIR=0 switches the preference off."""
+    """kernel="auto": two steps per pass when the hopping blocks are real-diagonal (DFMA rows) and a panel has 8
+    columns (or the lattice is small enough that narrow column sets are padded); single-step kernels otherwise;
+    BDG_AUTO_PAIR=0 switches the preference off."""
     scale = 10.0
     flat = cases.readme_swave(gpu_api, (12, 12, 1))._sys
-    for n_cols, want in ((8, "pair"), (19, "pair"), (5, "pair"), (4, "dict_diag"), (1, "dict_diag")):
+    for n_cols, want in ((8, "pair"), (19, "pair"), (5, "pair"), (4, "pair"), (1, "pair")):   # (small lattice: padded panels)
         flat.cheb_begin(n_random=n_cols, seed=1, scale=scale, kernel="auto")
         assert flat.cheb_format()["kernel"] == want
     monkeypatch.setenv("BDG_AUTO_PAIR", "0")
@@ -172,7 +184,7 @@ def test_t2_moments_match_the_oracle(gpu_api, monkeypatch, tag):
     scale = system.spectral_bound()
     for plan in PLANS[:4]:
         _set_plan(monkeypatch, plan)
-        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2), (8, 5), (6, 1), (8, 301)):
+        for n_cols, n_moments in ((8, 48), (5, 47), (19, 50), (12, 4), (8, 2), (8, 5), (6, 1), (8, 301), (4, 33), (1, 20), (3, 7)):
             got = system.chebyshev_moments(n_moments, vectors=n_cols, seed=3, scale=scale, kernel="t2")
             assert system._sys.cheb_format()["kernel"] == "t2"
             want = orc.cheb_moments(H, orc.rademacher(3, H.shape[0], np.arange(n_cols)), n_moments, scale)
@@ -254,7 +266,7 @@ def test_t2_observables_and_auto_moments(gpu_api):
         other.chebyshev_moments(16, vectors=8, seed=1)
         assert other._sys.cheb_format()["kernel"] == want
     system.chebyshev_moments(16, vectors=4, seed=1)
-    assert system._sys.cheb_format()["kernel"] == "dict_diag"
+    assert system._sys.cheb_format()["kernel"] == "t2"         # 1200 sites: four columns are padded to a panel
     with pytest.raises(ValueError):
         cases.swave_3d(gpu_api, (6, 5, 4))._sys.cheb_begin(n_random=8, seed=1, scale=10.0, kernel="t2")
 
