@@ -295,6 +295,38 @@ def cheb_moments_doubling(H, x0, n_moments, scale):
     return mu[:n_moments]
 
 
+def cheb_moments_even_vectors(H, x0, n_moments, scale):
+    """Same moments from the EVEN Chebyshev vectors alone -- the form the two-step CUDA kernel runs for callers
+    that only read moments (csrc/cheb_pair.cu MODE 1 + cheb.cu:t2_normalize; no reference code, like the
+    recursion itself).  With ``E_j = T_2j(H~) x0`` and ``u_j = H~ E_j``::
+
+        E_1 = 2 H~ u_0 - E_0,        E_{j+1} = 2 T_2(H~) E_j - E_{j-1} = 4 H~ u_j - 2 E_j - E_{j-1}
+
+    and from ``T_m T_n = (T_{m+n} + T_|m-n|) / 2`` the four dot products of a step give four moments::
+
+        a = <E_j,E_j> = (mu_4j + mu_0)/2                     c = <u_j,E_j> = (mu_{4j+1} + mu_{4j-1})/4 + mu_1/2
+        b = <E_{j+1},E_j> = (mu_{4j+2} + mu_2)/2             d = <E_{j+1},u_j> = (mu_{4j+3} + mu_{4j+1})/4 + (mu_3 + mu_1)/4
+    """
+    Ht = H / scale
+    dot = lambda x, y: np.einsum("rc,rc->c", x.conj(), y).real  # noqa: E731
+    n_launch = (n_moments + 3) // 4
+    mu = np.zeros((4 * n_launch, x0.shape[1]))
+    e_prev, e_cur = None, x0.copy()
+    for j in range(n_launch):
+        u = Ht @ e_cur
+        e_next = 2 * (Ht @ u) - e_cur if j == 0 else 4 * (Ht @ u) - 2 * e_cur - e_prev
+        a, c, b, d = dot(e_cur, e_cur), dot(u, e_cur), dot(e_next, e_cur), dot(e_next, u)
+        if j == 0:
+            mu[0], mu[1], mu[2], mu[3] = a, c, b, 2 * d - c
+        else:
+            mu[4 * j] = 2 * a - mu[0]
+            mu[4 * j + 2] = 2 * b - mu[2]
+            mu[4 * j + 1] = 4 * c - 2 * mu[1] - mu[4 * j - 1]
+            mu[4 * j + 3] = 4 * d - (mu[3] + mu[1]) - mu[4 * j + 1]
+        e_prev, e_cur = e_cur, e_next
+    return mu[:n_moments]
+
+
 def cheb_step(Ht, t_cur, t_prev):
     """One recursion step ``2*(H~ @ T_n) - T_{n-1}`` (the timed CPU baseline step)."""
     return 2 * (Ht @ t_cur) - t_prev

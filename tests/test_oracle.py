@@ -137,6 +137,12 @@ def test_moments_match_fixture_and_doubling(observables, structures, tag):
     assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
     dbl = orc.cheb_moments_doubling(H, x0, want.shape[0], scale)
     assert np.max(np.abs(dbl - want)) <= 1e-11 * np.max(np.abs(want))
+    # the even-vector form the two-step CUDA kernel runs (E_{j+1} = 2 T_2(H~) E_j - E_{j-1}, product identities),
+    # at every moment count modulo 4
+    for n in (want.shape[0], want.shape[0] - 1, want.shape[0] - 2, want.shape[0] - 3, 1, 2, 3, 4, 5):
+        even = orc.cheb_moments_even_vectors(H, x0, n, scale)
+        assert even.shape == (n, x0.shape[1])
+        assert np.max(np.abs(even - want[:n])) <= 1e-11 * np.max(np.abs(want))
 
 
 @pytest.mark.parametrize("tag", ["snf_10_7_3", "readme_12_12_1", "junction_30_10_1", "dwave_9_8_1"])
