@@ -172,6 +172,42 @@ def test_pair_follows_matrix_updates(gpu_api):
     assert rel_err(after, orc.cheb_moments(Hm, orc.rademacher(2, Hm.shape[0], np.arange(8)), 32, scale)) <= TOL
 
 
+def test_two_step_kernels_on_random_shapes_and_plans(monkeypatch):
+    """Seeded sweep over lattice extents (either plane orientation), patch sizes, segment lengths, CTA shapes, column
+    and step counts: pair vectors bit-identical to the single-step kernel, t2 vectors and moments to rounding."""
+    import bodge_b200 as b
+    from bodge_b200 import workloads
+
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        Lx, M = int(rng.integers(3, 70)), int(rng.integers(3, 90))
+        shape = (Lx, M, 1) if case % 3 else (Lx, 1, M)
+        build = workloads.junction if case % 2 else workloads.readme_swave
+        system = b.Hamiltonian(b.CubicLattice(shape))
+        assert system.fill(*build(shape)) == 0.0
+        scale = system.spectral_bound()
+        plan = (int(rng.integers(1, Lx + 3)) if rng.random() < 0.7 else None,
+                int(rng.integers(1, 31)) if rng.random() < 0.7 else None,
+                16 if rng.random() < 0.3 else None)
+        _set_plan(monkeypatch, plan)
+        n_cols, steps = int(rng.integers(1, 20)), int(rng.integers(1, 12))
+        (cur, prev), fmt = _vectors(system._sys, "pair", n_cols, steps, scale)
+        (want_cur, want_prev), _ = _vectors(system._sys, "dict_diag", n_cols, steps, scale)
+        assert fmt == "pair", (shape, plan)
+        assert np.array_equal(cur, want_cur) and np.array_equal(prev, want_prev), (shape, plan, n_cols, steps)
+        n_mom = 2 * steps + int(rng.integers(0, 3))
+        ref = system.chebyshev_moments(n_mom, vectors=n_cols, seed=9, scale=scale, kernel="dict_diag")
+        for kernel in ("pair", "t2"):
+            got = system.chebyshev_moments(n_mom, vectors=n_cols, seed=9, scale=scale, kernel=kernel)
+            assert rel_err(got, ref) <= 1e-12, (shape, plan, n_cols, n_mom, kernel)
+        sysn = system._sys
+        sysn.cheb_begin(n_random=n_cols, seed=5, col_offset=3, scale=scale, kernel="t2")
+        sysn.cheb_steps(2 * (steps // 2))                       # T_{2 (steps // 2) + 2}
+        t2_cur = sysn.cheb_vectors(n_cols, 0)
+        (want, _), _ = _vectors(sysn, "dict_diag", n_cols, 2 * (steps // 2) + 1, scale)
+        assert np.max(np.abs(t2_cur - want)) <= 1e-13 * max(np.max(np.abs(want)), 1.0), (shape, plan)
+
+
 # ---- the even-vector recursion (kernel="t2"): same kernel, E_{j+1} = 2 T_2(H~) E_j - E_{j-1} -------------------
 @pytest.mark.parametrize("tag", sorted(SYSTEMS))
 def test_t2_moments_match_the_oracle(gpu_api, monkeypatch, tag):
