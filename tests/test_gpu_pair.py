@@ -172,6 +172,31 @@ def test_pair_follows_matrix_updates(gpu_api):
     assert rel_err(after, orc.cheb_moments(Hm, orc.rademacher(2, Hm.shape[0], np.arange(8)), 32, scale)) <= TOL
 
 
+def test_one_call_c_entry_point(gpu_api):
+    """bdg_cheb_moments -- begin + steps + read in one ABI call -- only returns moments, so it runs the
+    even-vector recursion where that applies; checked at every moment count mod 4, per column and summed."""
+    import ctypes as C
+
+    from bodge_b200 import _native
+
+    lib = _native.load()
+    for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
+        H = system.matrix("bsr")
+        scale = system.spectral_bound()
+        x0 = orc.rademacher(77, H.shape[0], np.arange(8) + 2)
+        for n_moments in (1, 2, 3, 4, 5, 41, 42, 43, 44):
+            want = orc.cheb_moments(H, x0, n_moments, scale)
+            out = np.empty((n_moments, 8))
+            _native.check(lib.bdg_cheb_moments(system._sys._h, _native.X0_RADEMACHER, 8, None, 77, 2, C.c_double(scale),
+                                               n_moments, _native.MU_PER_COLUMN, out.ctypes.data_as(C.c_void_p), 0))
+            assert rel_err(out, want) <= TOL
+            total = np.empty(n_moments)
+            _native.check(lib.bdg_cheb_moments(system._sys._h, _native.X0_RADEMACHER, 8, None, 77, 2, C.c_double(scale),
+                                               n_moments, _native.MU_SUM, total.ctypes.data_as(C.c_void_p), 0))
+            assert rel_err(total, want.sum(axis=1)) <= TOL
+        assert system._sys.cheb_format()["kernel"] == want_kernel
+
+
 def test_two_step_kernels_on_random_shapes_and_plans(monkeypatch):
     """Seeded sweep over lattice extents (either plane orientation), patch sizes, segment lengths, CTA shapes, column
     and step counts: pair vectors bit-identical to the single-step kernel, t2 vectors and moments to rounding."""
