@@ -229,6 +229,12 @@ class Hamiltonian:
         is ``sum_c mu[n, c]`` (shape ``[moments]``).  When ``torch.distributed`` is initialised
         the columns are split over the ranks (each holds a replica of the matrix) and combined
         with one all-reduce / all-gather; every rank gets the full result.
+
+        ``kernel``: ``"auto"`` picks the fastest step kernel the matrix qualifies for (``include/bdg.h``): on 2-D
+        lattices with a few distinct blocks two applications of ``H`` per launch on the even Chebyshev vectors
+        (``"t2"``), else the block-dictionary / fixed-width / generic BSR single-step kernels (``"dict_diag"``,
+        ``"dict"``, ``"ell"``, ``"dmma"``); ``"pair"`` is the literal three-term recursion two steps per launch,
+        ``"fma"`` a scalar A/B reference.  All agree to rounding (tests: <= 1e-10 against the CPU oracle).
         """
         return self._columns(moments, lambda sysn, k: sysn.cheb_read(moments, k, summed=summed), summed,
                              rows=rows, vectors=vectors, seed=seed, scale=scale, kernel=kernel, batch=batch, group=group)
