@@ -315,8 +315,8 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 for (int s = 0; s < S; ++s) {
                     if (store && owned[s]) {
                         if (MODE == 0) tc[gout + 32 * s] = out[s];
-                        d0 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
-                        d1 += out[s].x * c[1 + s].x + out[s].y * c[1 + s].y;
+                        d0 = fma(c[1 + s].x, c[1 + s].x, fma(c[1 + s].y, c[1 + s].y, d0));
+                        d1 = fma(out[s].x, c[1 + s].x, fma(out[s].y, c[1 + s].y, d1));
                     }
                 }
             }
@@ -352,11 +352,11 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                     if (owned[s]) {
                         td[gout - gstep + 32 * s] = out;
                         if (MODE == 0) {
-                            d2 += c[1 + s].x * c[1 + s].x + c[1 + s].y * c[1 + s].y;
+                            d2 = fma(c[1 + s].x, c[1 + s].x, fma(c[1 + s].y, c[1 + s].y, d2));
                         } else {
-                            d2 += out.x * tn[s].x + out.y * tn[s].y;
+                            d2 = fma(out.x, tn[s].x, fma(out.y, tn[s].y, d2));
                         }
-                        d3 += out.x * c[1 + s].x + out.y * c[1 + s].y;
+                        d3 = fma(out.x, c[1 + s].x, fma(out.y, c[1 + s].y, d3));
                     }
                 }
             }
