@@ -273,7 +273,9 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         for (int q = tlo; q <= xlo; ++q) wait(q);
 
         for (int x = xlo; x <= x1; ++x, cidx += cstep, gout += gstep) {
-            // Plane x + kRingN - 3 replaces plane x - 3, last read by [A](x-2).
+            // Plane x + kRingN - 3 replaces plane x - 3, last read -- its own-site records -- by [B](x-3) in iteration
+            // x-2, which every warp finished before the barrier of iteration x-1 this thread has passed.  Plane x - 2
+            // is NOT free yet: [B](x-2) runs after that barrier and slower warps may still be in it.
             if (x > xlo) issue(x + kRingN - 3);
             double2 pv[S];
 #pragma unroll
