@@ -109,7 +109,7 @@ def check(rc: int):
 
 
 def release_cached(device: int = 0) -> None:
-    """Return the library's cache of released device buffers (>= 1 MiB each) to the CUDA driver."""
+    """Return the library's cache of released device buffers to the CUDA driver."""
     check(load().bdg_release_cached(int(device)))
 
 

@@ -25,12 +25,13 @@ void bdg_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-// Large device buffers are recycled through a per-device cache: cudaMalloc / cudaFree of the 1.3 GB
-// block array cost milliseconds each (page-table work), which is what creating or destroying a
-// 10^6-site Hamiltonian spent most of its time on.  BDG_CACHE_MB bounds the bytes held (0 = off).
+// Device buffers are recycled through a per-device cache: cudaMalloc / cudaFree of the 1.3 GB block array
+// cost milliseconds each (page-table work), and the dozen small allocations of a handle another 2-8 ms
+// together -- which is what creating or destroying a 10^6-site Hamiltonian spent most of its time on.
+// BDG_CACHE_MB bounds the bytes held (0 = off).
 namespace {
 constexpr int kMaxDevices = 16;
-constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr size_t kCacheMinBytes = 1;  // (small buffers too: a cudaMalloc / cudaFree pair costs more than the few bytes it manages)
 std::mutex g_cache_mutex;
 std::multimap<size_t, void *> g_cache[kMaxDevices];
 size_t g_cache_bytes[kMaxDevices] = {};

@@ -43,7 +43,7 @@ int bdg_abi_version(void);
 const char *bdg_last_error(void);
 int bdg_device_count(int *count);
 int bdg_destroy(bdg_t *sys);
-/* Device buffers of >= 1 MiB released by a handle are kept in a per-device cache and handed to the next
+/* Device buffers released by a handle are kept in a per-device cache and handed to the next
  * handle that asks for that size (cudaMalloc / cudaFree of a 1.3 GB block array cost milliseconds; the
  * reference has no counterpart -- numpy's allocator plays this role for its `_matrix.data`).  At most
  * BDG_CACHE_MB (default 8192, 0 = off) are held; this returns them to the driver. */
