@@ -17,6 +17,6 @@ for rep in range(3):
     print("call", rep)
     T("fill (H2D+scatter+check)", lambda: system.fill(*host))
     scale = T("spectral_bound", lambda: system.spectral_bound())
-    T("cheb_begin (formats+init)", lambda: s.cheb_begin(n_random=8, seed=1234, scale=scale, kernel="auto"))
+    T("cheb_begin (formats+init)", lambda: s.cheb_begin(n_random=8, seed=1234, scale=scale, kernel="auto_moments"))
     T("1024 steps", lambda: s.cheb_steps(1024))
     T("read moments", lambda: s.cheb_read(2050, 8, summed=True))
