@@ -102,10 +102,95 @@ def junction(shape, mu=-3.0, d0=0.2, phi=np.pi / 2, m=0.3, t=1.0):
     return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
 
 
+def _site_rng(seed, n):
+    """Counter-based per-site uniforms in [0, 1): the same numbers for every caller and lattice split."""
+    z = (np.arange(n, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def disordered_swave(shape, mu=-3.0, w=0.5, ds=0.2, t=1.0, seed=2024):
+    """Site-disordered s-wave superconductor: ``H[i,i] = -(mu + w (u_i - 1/2)) σ0``, ``Δ[i,i] = -ds (1/2 + v_i) jσ2``
+    with per-site uniforms ``u_i, v_i``, uniform hopping ``-t σ0``.  Every on-site block is distinct (a dictionary of
+    N + a few entries), the hopping blocks repeat: the "middle case" between the junction (7 distinct blocks) and
+    a fully random matrix -- disorder, a self-consistent Δ(r), the reference's phase-winding benchmark model."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    sites = np.arange(n, dtype=np.int64)
+    u, v = _site_rng(seed, n), _site_rng(seed + 1, n)
+    onsite = -(mu + w * (u - 0.5))[:, None, None] * σ0[None]
+    pair = (-ds * (0.5 + v))[:, None, None] * jσ2[None]
+    h_i, h_j, h_val = [sites], [sites], [onsite.astype(np.complex128)]
+    p_i, p_j, p_val = [sites], [sites], [pair.astype(np.complex128)]
+    for axis in (2, 1, 0):
+        i, j = _bonds(lat, axis)
+        h_i.append(i)
+        h_j.append(j)
+        h_val.append(_tile(-t * σ0, len(i)))
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
+def random_blocks(shape, mu=-3.0, ds=0.2, t=1.0, seed=77):
+    """Every stored block distinct: random on-site potential and gap as in ``disordered_swave`` AND a random
+    complex 2x2 hopping matrix on every bond (``H[j,i] = H[i,j]^†``) (bond disorder + random spin-orbit), open boundaries.  No block
+    repeats, so the step kernel streams the whole matrix: the case the SURVEY 8d roofline describes literally."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    h_i, h_j, h_val, p_i, p_j, p_val = (list(map(lambda a: [a], disordered_swave(shape, mu=mu, ds=ds, t=t, seed=seed)))[k] for k in range(6))
+    on = h_val[0][:n]
+    h_i, h_j, h_val = [h_i[0][:n]], [h_j[0][:n]], [on]
+    for axis in (2, 1, 0):
+        lo, hi = lat.bonds_array(axis)
+        m = len(lo)
+        r = [_site_rng(seed + 10 * (axis + 1) + c, m) - 0.5 for c in range(6)]
+        hop = np.zeros((m, 2, 2), dtype=np.complex128)
+        hop[:, 0, 0] = -t * (1 + 0.2 * r[0])
+        hop[:, 1, 1] = -t * (1 + 0.2 * r[1])
+        hop[:, 0, 1] = 0.2 * (r[2] + 1j * r[3])
+        hop[:, 1, 0] = 0.2 * (r[4] + 1j * r[5])
+        h_i += [lo, hi]
+        h_j += [hi, lo]
+        h_val += [hop, np.conj(np.transpose(hop, (0, 2, 1)))]   # H[j,i] = H[i,j]^†
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
+def benchmark_bilayer(shape, mu=0.5, d0=1.0, m0=1.5, chi=0.5, t=1.0):
+    """The reference's own assembly benchmark model (misc/benchmark.py:96-128): superconductor with a phase
+    winding ``Δ0 exp(i χ x / L)`` on the left half, ferromagnet on the right half, hopping ``-t σ0`` along x and
+    ``-2t σ0`` along y."""
+    lat = CubicLattice(shape)
+    n = lat.size
+    Lx, Ly, Lz = shape
+    sites = np.arange(n, dtype=np.int64)
+    x_of = sites // (Ly * Lz)
+    left = x_of < Lx // 2
+    onsite = _tile(-mu * σ0, n)
+    onsite[~left] = -mu * σ0 - m0 * σ3
+    h_i, h_j, h_val = [sites], [sites], [onsite]
+    s_sites = sites[left]
+    phase = np.exp(1j * chi * x_of[left] / Lx)
+    p_i, p_j, p_val = [s_sites], [s_sites], [(-d0 * phase)[:, None, None] * jσ2[None]]
+    for axis, amp in ((0, -t), (1, -2 * t)):
+        i, j = _bonds(lat, axis)
+        h_i.append(i)
+        h_j.append(j)
+        h_val.append(_tile(amp * σ0, len(i)))
+    return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
+
+
 CONFIGS = {
     "C1": dict(shape=(40, 40, 1), build=readme_swave, label="CubicLattice((40,40,1)) README s-wave"),
     "C2": dict(shape=(100, 100, 1), build=readme_swave, label="CubicLattice((100,100,1)) README s-wave + spin splitting"),
     "C3": dict(shape=(100, 100, 1), build=dwave_rashba, label="CubicLattice((100,100,1)) d-wave + Rashba SOC"),
     "C4": dict(shape=(64, 64, 64), build=swave_3d, label="CubicLattice((64,64,64)) 3D s-wave"),
     "C5": dict(shape=(1000, 1000, 1), build=junction, label="CubicLattice((1000,1000,1)) altermagnet/SC Josephson junction"),
+    # the same 10^6-site lattice with less and less block repetition (VERDICT r1: the headline must not depend on 7 repeating blocks)
+    "C5_disordered": dict(shape=(1000, 1000, 1), build=disordered_swave,
+                          label="CubicLattice((1000,1000,1)) s-wave with site-disordered potential and gap (10^6 distinct on-site blocks)"),
+    "C5_random": dict(shape=(1000, 1000, 1), build=random_blocks,
+                      label="CubicLattice((1000,1000,1)) every block distinct (random on-site terms and random Hermitian hopping)"),
+    "C5_bilayer": dict(shape=(1024, 1024, 1), build=benchmark_bilayer,
+                       label="CubicLattice((1024,1024,1)) S/F bilayer with phase winding (the reference's misc/benchmark.py model)"),
 }

@@ -149,3 +149,23 @@ def time_steps(indptr, indices, data, scale, x0, steps, warmup, budget_s=60.0, n
         stepper.close()
     return dict(ms_per_step=1e3 * elapsed / steps / covered, fraction=covered, cores=cores,
                 full_step_s=t_full, elapsed_s=elapsed)
+
+
+def moments_parallel(indptr, indices, data, scale, x0, n_moments, n_procs=None):
+    """``mu[n, c] = <x0_c| T_n(H/scale) |x0_c>`` for ``n < n_moments`` by the literal three-term recursion
+    (``bdg_oracle.cheb_moments``: same arithmetic, scipy ``bsr_matvecs``), with the block rows split over the host
+    cores so that a 10^6-site check takes seconds.  The CHECKER of the full-size parity tests and of ``bench.py``'s
+    ``parity_check``."""
+    x0 = np.ascontiguousarray(x0, dtype=np.complex128)
+    mu = np.empty((n_moments, x0.shape[1]))
+    stepper = ParallelStepper(indptr, indices, data, scale, x0, n_procs=n_procs, row_fraction=1.0)
+    try:
+        mu[0] = np.einsum("ic,ic->c", x0.conj(), x0).real
+        if n_moments > 1:
+            mu[1] = np.einsum("ic,ic->c", x0.conj(), stepper.current()).real
+        for n in range(2, n_moments):
+            stepper.step()
+            mu[n] = np.einsum("ic,ic->c", x0.conj(), stepper.current()).real
+    finally:
+        stepper.close()
+    return mu
