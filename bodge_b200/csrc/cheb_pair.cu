@@ -33,6 +33,7 @@
 // the dot products are summed over a different partition of the rows (agree to rounding).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
@@ -100,17 +101,18 @@ __device__ __forceinline__ void pin(uint32_t &v) { asm volatile("" : "+r"(v)); }
 
 // B fragments of the S rows a warp handles (cheb_ell.cu: DICT / DIAG), held in registers from plane to
 // plane and reloaded only when a code differs from the held one.  Lane s * 5 + u carries the code of
-// row s, direction u; code < 0 = no block.
-template <bool DIAG, int S>
+// row s, direction u; code < 0 = no block.  SELF: the on-site fragments (u = 0) are not held -- they are
+// fetched per row, one plane ahead (self_fragments) -- so their codes do not take part in the test.
+template <bool DIAG, bool SELF, int S>
 __device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[S][kDirs], const double *__restrict__ table,
-                                               const double *__restrict__ dtab, int lane) {
-    const unsigned changed = __ballot_sync(kFull, jv != jheld);
+                                               const double *__restrict__ dtab, int lane, bool self_lane) {
+    const unsigned changed = __ballot_sync(kFull, jv != jheld && !(SELF && self_lane));
     if (changed) {
         jheld = jv;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
 #pragma unroll
-            for (int u = 0; u < kDirs; ++u) {
+            for (int u = SELF ? 1 : 0; u < kDirs; ++u) {
                 const int code = __shfl_sync(kFull, jv, s * kDirs + u);
                 const unsigned take = changed >> (s * kDirs + u) & 1u;
                 const size_t c = (size_t)max(code, 0);
@@ -122,14 +124,28 @@ __device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep
     }
 }
 
+// SELF: this lane's double of the on-site B fragment of row s, straight from the table by the row's code
+// (-1: no diagonal block -> 0).  Issued a plane ahead of its use; with every on-site block distinct (disorder,
+// self-consistent gap) this is the 256-byte-per-site stream the matrix cannot do without, with a phase winding
+// or a layered structure it hits in L1 / L2.
+template <int S>
+__device__ __forceinline__ void self_fragments(int jv, double (&f)[S], const double *__restrict__ table, int lane) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int code = __shfl_sync(kFull, jv, s * kDirs);
+        f[s] = 0.0;
+        ld_table_pred(f[s], table + (size_t)max(code, 0) * 32 + lane, code >= 0);
+    }
+}
+
 // y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell
 // (directions: self, x-1, y-1, y+1, x+1 = ascending block column).
 template <bool DIAG>
 __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1, const double2 &x2, const double2 &x3,
-                                            const double2 &x4, const double (&bop)[kDirs], double &yr, double &yi) {
+                                            const double2 &x4, double b0, const double (&bop)[kDirs], double &yr, double &yi) {
     double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
-    dmma_8x8x4(a10, a11, x0.x, bop[0]);
-    dmma_8x8x4(a20, a21, x0.y, bop[0]);
+    dmma_8x8x4(a10, a11, x0.x, b0);
+    dmma_8x8x4(a20, a21, x0.y, b0);
     if (!DIAG) {
         dmma_8x8x4(a10, a11, x1.x, bop[1]);
         dmma_8x8x4(a20, a21, x1.y, bop[1]);
@@ -159,13 +175,23 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
 // planes of W records (T_{n+1}), two guard records, one mbarrier per T_n plane: 105 KB at NW = 8, so two
 // CTAs share an SM (one computes while the other waits at its barrier).
 //
-// The matrix arrives as `dcode[row][5]`: the dictionary code of the row's block in each stencil
-// direction (self, x-1, y-1, y+1, x+1; -1 = none), so the records a row needs sit at fixed offsets from
-// its own in the rings -- no per-row index arithmetic, and the two sites of a warp share their
-// in-plane neighbours (4 loads for 6 operands).  A direction without a lattice site (boundary) is read
-// all the same and meets a zero fragment: the rings are cleared once, so whatever sits there is an
-// earlier, finite, vector value.  Warps whose site does not exist (ragged last patch) compute on
-// whatever the rings hold and store nothing: the row body has no branches.
+// Geometry is a TORUS: planes x and in-plane sites y are taken modulo Lx and M, so the halo of the first /
+// last patch and of the first / last segment is the opposite face of the lattice (staged by its own small bulk
+// copy).  What is connected is decided by the matrix alone: it arrives as `dcode[row][5]`, the dictionary code
+// of the row's block in each stencil direction (self, x-1, y-1, y+1, x+1; -1 = none), so the reference's
+// periodic skeleton with the edges filled in (bodge/lattice.py:161-197) and the open lattice it leaves when they
+// are not run the same code: a direction without a block meets a zero fragment (whatever finite vector value
+// sits at the wrapped position is multiplied by zero; the rings are cleared once).  The records a row needs sit
+// at fixed offsets from its own in the rings -- no per-row index arithmetic -- and the two sites of a warp
+// share their in-plane neighbours (4 loads for 6 operands).  Warps whose site does not exist (ragged last patch)
+// compute on whatever the rings hold and store nothing: the row body has no branches.
+//
+// An item = (patch, segment [x0, x0 + len)).  Iteration i = 0 .. len + 1 of an item:
+//   [A] plane x0 - 1 + i from the T_n planes t = i, i + 1, i + 2 of the item (t <-> plane x0 - 2 + t);
+//       stored / counted in the dot products for 1 <= i <= len
+//   [B] plane x0 - 2 + i (i >= 2) from the T_{n+1} planes of iterations i - 2, i - 1, i
+// T_n planes occupy ring slots in the order they are consumed, across items (`cnt`): slot = count & 7, mbarrier
+// parity = (count >> 3) & 1.
 //
 // MODE 1 ("T2", the doubled-argument recursion) runs the same two sub-steps on the EVEN vectors only:
 //     E_j = T_2j(H~) x,   E_{j+1} = 2 T_2(H~) E_j - E_{j-1} = 4 H~ (H~ E_j) - 2 E_j - E_{j-1}
@@ -174,13 +200,14 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
 //     a = <E_j, E_j>, c = <u, E_j>, b = <E_{j+1}, E_j>, d = <E_{j+1}, u>
 // from which the same four moments follow (cheb.cu: t2_normalize), but it moves THREE vector passes instead
 // of four, and two vector buffers suffice.  `first`: E_1 = T_2(H~) E_0 = 2 H~ u - E_0 (E_{-1} = E_1).
-template <bool DIAG, int NW, int S, int MINB, int MODE>
+template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
                double2 *__restrict__ xc /* T_{n+1} */, double2 *__restrict__ xd /* T_{n+2} */, int n_sites, int n_panels,
-               double alpha, double alpha2, int first, double *__restrict__ partials, unsigned *__restrict__ tickets,
+               double alpha, double alpha2, double csub, int first, double *__restrict__ partials, unsigned *__restrict__ tickets,
                double *__restrict__ dots_step, const PairWalk wk) {
+    // MODE 1: E_{j+1} = alpha2 H~u - (csub E_j + E_{j-1}); csub = 2, or 1 in the first launch, where E_{-1} is never loaded (= 0)
     constexpr int W = NW * S, R = kRecBytes;
     constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
     extern __shared__ __align__(128) unsigned char pair_smem[];
@@ -193,11 +220,6 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const size_t pbase = (size_t)panel * n_sites * 32;
     const double2 *ta = xa + pbase, *tb = xb + pbase;
     double2 *tc = xc + pbase, *td = xd + pbase;  // MODE 1: td = ta (E_{j+1} over E_{j-1}), tc unused
-    const int l0 = S * warp;  // this warp's sites: l0, l0 + 1
-    // own-record addresses of site l0 in slot 0 of each ring (+ lane's 16 bytes)
-    uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
-    uint32_t a1 = sT1 + (uint32_t)l0 * R + (uint32_t)lane * 16u;
-    pin(aN), pin(a1);
 
     for (uint32_t o = threadIdx.x * 16u; o < kRingN * PLANE_N + kRing * PLANE_W + 2 * R; o += NW * 32 * 16u)
         sts_rec(sTn + o, make_double2(0.0, 0.0));
@@ -208,163 +230,217 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
     __syncthreads();
-    uint32_t phases = 0;  // bit r = parity of the next completion of ring slot r
-
+    uint32_t cnt = 0;  // T_n planes consumed by the items before this one
+    const size_t gstep = (size_t)wk.M * 32;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+
+    {
+    const int l0 = S * warp;  // this warp's sites: l0, l0 + 1
+    // own-record addresses of site l0 in slot 0 of each ring (+ lane's 16 bytes)
+    uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
+    uint32_t a1 = sT1 + (uint32_t)l0 * R + (uint32_t)lane * 16u;
+    pin(aN), pin(a1);
     double keep[S][kDirs];
     int jheld = -2;
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int u = 0; u < kDirs; ++u) keep[s][u] = 0.0;
-    const int code_last = n_sites * kDirs - 1;
+    // lanes 0 .. 5 S - 1 carry the codes of the warp's rows: lane = s * 5 + direction
+    const int csite = lane / kDirs, cdir = lane - csite * kDirs;
+    const bool code_lane = lane < S * kDirs, self_lane = cdir == 0;
+    const int plane_codes = wk.M * kDirs, all_codes = wk.Lx * plane_codes;
 
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
         const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
-        const int y0 = patch * wk.P, x0 = seg * wk.seg_len, x1 = min(wk.Lx, x0 + wk.seg_len);
-        const int xlo = max(0, x0 - 1), xhi = min(wk.Lx, x1 + 1);    // planes of sub-step [A]
-        const int tlo = max(0, xlo - 1), thi = min(wk.Lx, xhi + 1);  // T_n planes they read
-        const int nlo = max(0, y0 - 2), nhi = min(wk.M, y0 + wk.P + 2);  // in-plane run of T_n
-
-        // T_n plane q -> ring slot q % kRingN, one barrier phase per plane.
-        auto issue = [&](int q) {
-            if (threadIdx.x == 0 && q < thi) {
-                const int r = q & (kRingN - 1);
-                const uint32_t nbytes = (uint32_t)(nhi - nlo) * R;
-                mbar_expect_tx(sBar + 8 * r, nbytes);
-                bulk_g2s(sTn + r * PLANE_N + (uint32_t)(nlo - (y0 - 2)) * R, tb + ((size_t)q * wk.M + nlo) * 32, nbytes,
-                         sBar + 8 * r);
+        const int y0 = patch * wk.P, x0 = seg * wk.seg_len, len = min(wk.Lx, x0 + wk.seg_len) - x0;
+        const int n_planes = len + 4;  // T_n planes x0 - 2 .. x0 + len + 1 (mod Lx); plane t -> ring slot (cnt + t) % kRingN
+        // In-plane run of a T_n plane: y = y0 - 2 .. ye + 1 (ye = end of the owned sites), l2 = y - (y0 - 2); the part
+        // below 0 / from M on comes from the opposite side of the plane (its own small bulk copy).
+        const int ye = min(wk.M, y0 + wk.P), span = ye - y0 + 4;
+        const int n_lo = max(0, 2 - y0), n_hi = max(0, ye + 2 - wk.M);
+        const double2 *src_lo = tb + (ptrdiff_t)(y0 - 2 + wk.M) * 32, *src_main = tb + (ptrdiff_t)(y0 - 2 + n_lo) * 32,
+                      *src_hi = tb + (ptrdiff_t)(ye + 2 - n_hi - wk.M) * 32;
+        // One elected thread stages a plane: expect the bytes on the slot's barrier, then up to three bulk copies.
+        auto issue = [&](int t) {
+            if (warp == 0 && t < n_planes) {
+                int xw = x0 - 2 + t;
+                xw += xw < 0 ? wk.Lx : 0;
+                xw -= xw >= wk.Lx ? wk.Lx : 0;
+                const size_t po = (size_t)xw * gstep;
+                const uint32_t r = (cnt + (uint32_t)t) & (kRingN - 1);
+                const uint32_t dst = sTn + r * PLANE_N, bar = sBar + 8 * r;
+                if (lane == 0) {
+                    mbar_expect_tx(bar, (uint32_t)span * R);
+                    bulk_g2s(dst + (uint32_t)n_lo * R, src_main + po, (uint32_t)(span - n_lo - n_hi) * R, bar);
+                    if (n_lo) bulk_g2s(dst, src_lo + po, (uint32_t)n_lo * R, bar);
+                    if (n_hi) bulk_g2s(dst + (uint32_t)(span - n_hi) * R, src_hi + po, (uint32_t)n_hi * R, bar);
+                }
             }
         };
-        auto wait = [&](int q) {
-            if (q < thi) {
-                const int r = q & (kRingN - 1);
-                mbar_wait(sBar + 8 * r, (phases >> r) & 1u);
-                phases ^= 1u << r;
+        auto wait = [&](int t) {
+            if (t < n_planes) {
+                const uint32_t c = cnt + (uint32_t)t;
+                mbar_wait(sBar + 8 * (c & (kRingN - 1)), (c >> 3) & 1u);
             }
         };
 
         __syncthreads();  // every warp is done with the previous item's planes
-        for (int q = tlo; q <= xlo + kRingN - 3; ++q) issue(q);
+        for (int t = 0; t < kRingN; ++t) issue(t);
 
-        // Site l0 + s of this warp: y = y0 - 1 + l0 + s.  Owned = inside the patch and the lattice.
+        // Site l0 + s of this warp: y = y0 - 1 + l0 + s (mod M).  Owned = inside the patch and the lattice.
         const int ya = y0 - 1 + l0;
         bool owned[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) owned[s] = l0 + s >= 1 && l0 + s <= wk.P && ya + s < wk.M;
-        // lanes 0..9: the codes of the warp's two rows are ten consecutive ints of dcode
-        int cidx = (xlo * wk.M + ya) * kDirs + lane;
-        const int cstep = wk.M * kDirs;
+        // code index of this lane's (row, direction) in plane 0; rows past the halo (ragged patch) wrap anywhere valid
+        int yl = (ya + csite) % wk.M;
+        yl += yl < 0 ? wk.M : 0;
+        const int coff = yl * kDirs + cdir;
+        int cplane = x0 - 1;  // plane of [A] in iteration 0
+        cplane += cplane < 0 ? wk.Lx : 0;
+        cplane *= plane_codes;
         int jvA = -1, jvB = -1;
-        if (lane < S * kDirs) jvA = __ldg(dcode + min(max(cidx, 0), code_last));
-        size_t gout = ((size_t)xlo * wk.M + ya) * 32 + lane;  // T_{n+1}(x, ya); the second row 32 elements on
-        const size_t gstep = (size_t)wk.M * 32;
-        // T_{n-1} of the warp's two rows goes straight to registers, one plane ahead (read once, by
-        // this warp only: nothing to share through shared memory).
-        bool prev_ok[S];
+        if (code_lane) jvA = __ldg(dcode + cplane + coff);
+        double fsA[S], fsB[S], fsN[S];  // SELF: on-site fragments of the planes of [A], [B] and of the next [A]
 #pragma unroll
-        for (int s = 0; s < S; ++s) prev_ok[s] = l0 + s < wk.P + 2 && ya + s >= 0 && ya + s < wk.M;
-        double2 pvn[S];
+        for (int s = 0; s < S; ++s) fsA[s] = fsB[s] = fsN[s] = 0.0;
+        if (SELF) self_fragments<S>(jvA, fsA, table, lane);
+        // Global element of (plane x0 - 1, site ya): T_{n+1} / E_{j-1} / E_{j+1} of the warp's rows; only owned rows of
+        // owned planes are dereferenced through it.  The second row sits 32 elements on.
+        const ptrdiff_t gbase = ((ptrdiff_t)(x0 - 1) * wk.M + ya) * 32 + lane;
+        const double2 *pin_ = ta + gbase;                       // MODE 1: E_{j-1}(plane of [A])
+        double2 *pout1 = tc + gbase;                            // MODE 0: T_{n+1}(plane of [A])
+        double2 *pout2 = td + gbase - (ptrdiff_t)gstep;         // T_{n+2} / E_{j+1}(plane of [B]) = one plane behind [A]
+        // MODE 0: T_{n-1} of ALL rows [A] computes (halo rows and halo planes included), wrapped like the codes;
+        // MODE 1: E_{j-1} of the owned rows of the plane [B] works on, loaded right after the previous [B] used the registers.
+        int yw[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pvn[s] = make_double2(0.0, 0.0);
-            if (MODE == 0 && prev_ok[s]) pvn[s] = ld_prev(ta + gout + 32 * s);
+            yw[s] = (ya + s) % wk.M;
+            yw[s] += yw[s] < 0 ? wk.M : 0;
         }
-        for (int q = tlo; q <= xlo; ++q) wait(q);
+        int xprev = x0 - 1;  // wrapped plane of [A]
+        xprev += xprev < 0 ? wk.Lx : 0;
+        double2 pv[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            pv[s] = make_double2(0.0, 0.0);
+            if (MODE == 0) pv[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
+        }
+        wait(0);
+        wait(1);
 
-        for (int x = xlo; x <= x1; ++x, cidx += cstep, gout += gstep) {
-            // Plane x + kRingN - 3 replaces plane x - 3, last read -- its own-site records -- by [B](x-3) in iteration
-            // x-2, which every warp finished before the barrier of iteration x-1 this thread has passed.  Plane x - 2
-            // is NOT free yet: [B](x-2) runs after that barrier and slower warps may still be in it.
-            if (x > xlo) issue(x + kRingN - 3);
-            double2 pv[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                pv[s] = pvn[s];
-                if (MODE == 0) {
-                    if (x + 1 < xhi && prev_ok[s]) pvn[s] = ld_prev(ta + gout + gstep + 32 * s);
-                } else {  // E_{j-1}(x, y) for [B](x) of the next iteration; this thread overwrites it there
-                    if (x >= x0 && x < x1 && owned[s] && !first) pvn[s] = ld_prev_rw(ta + gout + 32 * s);
-                }
-            }
-            wait(x + 1);
-            const bool do_a = x < xhi;
+        for (int i = 0; i <= len + 1; ++i, pin_ += gstep, pout1 += gstep, pout2 += gstep) {
+            const bool store = i >= 1 && i <= len;
+            wait(i + 2);
             int jnext = -1;
-            if (do_a && x + 1 < xhi && lane < S * kDirs) jnext = __ldg(dcode + min(max(cidx + cstep, 0), code_last));
-            if (do_a) {
-                const bool store = x >= x0 && x < x1;
-                const uint32_t n0 = aN + (uint32_t)(x & (kRingN - 1)) * PLANE_N;
-                const uint32_t nm = aN + (uint32_t)((x - 1) & (kRingN - 1)) * PLANE_N;
-                const uint32_t np = aN + (uint32_t)((x + 1) & (kRingN - 1)) * PLANE_N;
-                hold_fragments<DIAG, S>(jvA, jheld, keep, table, dtab, lane);
-                double2 c[S + 2], m[S], q[S], out[S];  // c[1 + s] = the own record of site s; c[0], c[S + 1] = the warp's in-plane neighbours
+            cplane += plane_codes;
+            cplane -= cplane >= all_codes ? all_codes : 0;
+            if (code_lane && i <= len) jnext = __ldg(dcode + cplane + coff);
+            if (SELF) self_fragments<S>(jnext, fsN, table, lane);
+            double2 tn[S];  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
+            {
+                const uint32_t c = cnt + (uint32_t)i;
+                const uint32_t nm = aN + (c & (kRingN - 1)) * PLANE_N;
+                const uint32_t n0 = aN + ((c + 1) & (kRingN - 1)) * PLANE_N;
+                const uint32_t np = aN + ((c + 2) & (kRingN - 1)) * PLANE_N;
+                hold_fragments<DIAG, SELF, S>(jvA, jheld, keep, table, dtab, lane, self_lane);
+                double2 c_[S + 2], q[S], out[S];  // c_[1 + s] = the own record of site s; c_[0], c_[S + 1] = the warp's in-plane neighbours
 #pragma unroll
-                for (int i = 0; i < S + 2; ++i) c[i] = lds_rec(n0 + (uint32_t)(i - 1) * R);
+                for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(n0 + (uint32_t)(k - 1) * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) m[s] = lds_rec(nm + (uint32_t)s * R);
+                for (int s = 0; s < S; ++s) tn[s] = lds_rec(nm + (uint32_t)s * R);
 #pragma unroll
                 for (int s = 0; s < S; ++s) q[s] = lds_rec(np + (uint32_t)s * R);
-                const uint32_t t1 = a1 + (uint32_t)(x & (kRing - 1)) * PLANE_W;
+                const uint32_t t1 = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
-                    row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
+                    row_product<DIAG>(c_[1 + s], tn[s], c_[s], c_[2 + s], q[s], SELF ? fsA[s] : keep[s][0], keep[s], yr, yi);
                     if (MODE == 0) out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
                     else out[s] = make_double2(alpha * yr, alpha * yi);
                     sts_rec(t1 + (uint32_t)s * R, out[s]);
                 }
+                if (store) {
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    if (store && owned[s]) {
-                        if (MODE == 0) tc[gout + 32 * s] = out[s];
-                        d0 = fma(c[1 + s].x, c[1 + s].x, fma(c[1 + s].y, c[1 + s].y, d0));
-                        d1 = fma(out[s].x, c[1 + s].x, fma(out[s].y, c[1 + s].y, d1));
+                    for (int s = 0; s < S; ++s) {
+                        if (owned[s]) {
+                            if (MODE == 0) pout1[32 * s] = out[s];
+                            d0 = fma(c_[1 + s].x, c_[1 + s].x, fma(c_[1 + s].y, c_[1 + s].y, d0));
+                            d1 = fma(out[s].x, c_[1 + s].x, fma(out[s].y, c_[1 + s].y, d1));
+                        }
                     }
+                }
+                if (MODE == 0 && i <= len) {  // T_{n-1} of the next plane of [A]
+                    xprev += 1;
+                    xprev -= xprev >= wk.Lx ? wk.Lx : 0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) pv[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
                 }
             }
-            __syncthreads();  // T_{n+1}(x) complete in the ring
-            if (x - 1 >= x0) {
-                const int xb1 = x - 1;
-                const uint32_t t0 = a1 + (uint32_t)(xb1 & (kRing - 1)) * PLANE_W;
-                const uint32_t tm = a1 + (uint32_t)((xb1 - 1) & (kRing - 1)) * PLANE_W;
-                const uint32_t tp = a1 + (uint32_t)((xb1 + 1) & (kRing - 1)) * PLANE_W;
-                hold_fragments<DIAG, S>(jvB, jheld, keep, table, dtab, lane);
-                double2 c[S + 2], m[S], q[S], tn[S];
+            __syncthreads();  // T_{n+1} of this plane complete in the ring
+            // ... and [A] is done in every warp: plane i (its x-1 neighbours) is dead, its slot takes plane i + 8 -- seven
+            // planes in flight beyond the one in use.
+            issue(i + kRingN);
+            if (i >= 2) {
+                const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
+                const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
+                const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
+                // Only owned rows have a [B]; the rim warps of a patch (and of a ragged last patch) own one site or none.
+                // Specialised on which of the warp's sites are live so that two live sites stay interleaved.
+                auto sub_b = [&](auto live0, auto live1) {
+                    constexpr bool live[2] = {decltype(live0)::value, decltype(live1)::value};
+                    double2 c_[S + 2], m[S], q[S];
 #pragma unroll
-                for (int i = 0; i < S + 2; ++i) c[i] = lds_rec(t0 + (uint32_t)(i - 1) * R);
+                    for (int k = 0; k < S + 2; ++k)
+                        if ((k >= 1 && live[k - 1]) || (k < S && live[k]) || (k >= 2 && live[k - 2])) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+                    for (int s = 0; s < S; ++s)
+                        if (live[s]) m[s] = lds_rec(tm + (uint32_t)s * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
-                // T_n(x-1) of the warp's rows: its plane stays in the T_n ring until iteration x+2 issues over it
-                const uint32_t nb = aN + (uint32_t)(xb1 & (kRingN - 1)) * PLANE_N;
+                    for (int s = 0; s < S; ++s)
+                        if (live[s]) q[s] = lds_rec(tp + (uint32_t)s * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) tn[s] = lds_rec(nb + (uint32_t)s * R);
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    double yr, yi;
-                    row_product<DIAG>(c[1 + s], m[s], c[s], c[2 + s], q[s], keep[s], yr, yi);
-                    double2 out;
-                    if (MODE == 0) {
-                        out = make_double2(fma(alpha, yr, -tn[s].x), fma(alpha, yi, -tn[s].y));
-                    } else {
-                        const double2 sub = first ? tn[s] : make_double2(fma(2.0, tn[s].x, pv[s].x), fma(2.0, tn[s].y, pv[s].y));
-                        out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
-                    }
-                    if (owned[s]) {
-                        td[gout - gstep + 32 * s] = out;
+                    for (int s = 0; s < S; ++s) {
+                        if (!live[s]) continue;
+                        double yr, yi;
+                        row_product<DIAG>(c_[1 + s], m[s], c_[s], c_[2 + s], q[s], SELF ? fsB[s] : keep[s][0], keep[s], yr, yi);
+                        const double2 t = tn[s];
+                        double2 out;
                         if (MODE == 0) {
-                            d2 = fma(c[1 + s].x, c[1 + s].x, fma(c[1 + s].y, c[1 + s].y, d2));
+                            out = make_double2(fma(alpha, yr, -t.x), fma(alpha, yi, -t.y));
                         } else {
-                            d2 = fma(out.x, tn[s].x, fma(out.y, tn[s].y, d2));
+                            const double2 sub = make_double2(fma(csub, t.x, pv[s].x), fma(csub, t.y, pv[s].y));
+                            out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
                         }
-                        d3 = fma(out.x, c[1 + s].x, fma(out.y, c[1 + s].y, d3));
+                        pout2[32 * s] = out;
+                        if (MODE == 0) {
+                            d2 = fma(c_[1 + s].x, c_[1 + s].x, fma(c_[1 + s].y, c_[1 + s].y, d2));
+                        } else {
+                            d2 = fma(out.x, t.x, fma(out.y, t.y, d2));
+                        }
+                        d3 = fma(out.x, c_[1 + s].x, fma(out.y, c_[1 + s].y, d3));
                     }
-                }
+                };
+                static_assert(S == 2, "sub_b is specialised for two sites per warp");
+                if (owned[0] || owned[1]) hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
+                if (owned[0] && owned[1]) sub_b(std::true_type{}, std::true_type{});
+                else if (owned[0]) sub_b(std::true_type{}, std::false_type{});
+                else if (owned[1]) sub_b(std::false_type{}, std::true_type{});
+            }
+            if (MODE == 1 && store && !first) {  // E_{j-1} of this plane: [B] of the next iteration works on it (and overwrites it)
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (owned[s]) pv[s] = ld_prev_rw(pin_ + 32 * s);
             }
             jvB = jvA;
             jvA = jnext;
+#pragma unroll
+            for (int s = 0; s < S; ++s) fsB[s] = fsA[s], fsA[s] = fsN[s];
         }
+        cnt += (uint32_t)n_planes;
+    }
     }
 
     // ---- the four dot products of the two steps: quad -> warp -> CTA -> last CTA, fixed order ----
@@ -416,43 +492,59 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     if (threadIdx.x == 0) tickets[panel] = 0u;
 }
 
-// *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its four
-// nearest neighbours in the (x, in-plane) grid, without wrap-around.
+// Stencil direction of block column `col` seen from `row` on the Lx x M torus: 0 = the row itself, 1 = x-1,
+// 2 = y-1, 3 = y+1, 4 = x+1 (wrap-around included), -1 = none of these.  Lx, M >= 3 keep the five apart.
+__device__ __forceinline__ int torus_direction(int row, int col, int Lx, int M) {
+    const int xr = row / M, yr = row - xr * M, xc = col / M, yc = col - xc * M;
+    int dx = xc - xr, dy = yc - yr;
+    dx += dx < 0 ? Lx : 0;
+    dy += dy < 0 ? M : 0;
+    if (dx == 0) return dy == 0 ? 0 : (dy == M - 1 ? 2 : (dy == 1 ? 3 : -1));
+    if (dy != 0) return -1;
+    return dx == Lx - 1 ? 1 : (dx == 1 ? 4 : -1);
+}
+
+// *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its four nearest
+// neighbours on the (x, in-plane) torus -- the open stencil and the reference's periodic one both qualify.
 __global__ void __launch_bounds__(256)
-pair_check(int64_t n_slots, int width, int M, const int32_t *__restrict__ cidx, int *__restrict__ bad) {
+pair_check(int64_t n_slots, int width, int Lx, int M, const int32_t *__restrict__ cidx, int *__restrict__ bad) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_slots) return;
-    const int row = (int)(t / width), d = cidx[t] - row, m = row % M;
-    const bool ok = d == 0 || d == M || d == -M || (d == 1 && m != M - 1) || (d == -1 && m != 0);
-    if (!ok) *bad = 1;
+    const int row = (int)(t / width);
+    if (torus_direction(row, cidx[t], Lx, M) < 0) *bad = 1;
 }
 
 // dcode[row][dir] = dictionary code of the row's block towards (self, x-1, y-1, y+1, x+1), -1 = none.
 // Slot 0 of the fixed-width copy is the diagonal block; padding slots point at the row itself.
 __global__ void __launch_bounds__(256)
-pair_codes(int n_sites, int width, int M, const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode,
+pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode,
            int32_t *__restrict__ dcode) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_sites) return;
     int out[kDirs] = {-1, -1, -1, -1, -1};
     for (int u = 0; u < width; ++u) {
-        const int d = cidx[(size_t)row * width + u] - row, c = ccode[(size_t)row * width + u];
+        const int c = ccode[(size_t)row * width + u];
+        const int d = u == 0 ? 0 : torus_direction(row, cidx[(size_t)row * width + u], Lx, M);
         if (u == 0) out[0] = c;
-        else if (d == -M) out[1] = c;
-        else if (d == -1) out[2] = c;
-        else if (d == 1) out[3] = c;
-        else if (d == M) out[4] = c;
+        else if (d == 1) out[1] = c;
+        else if (d == 2) out[2] = c;
+        else if (d == 3) out[3] = c;
+        else if (d == 4) out[4] = c;
     }
 #pragma unroll
     for (int k = 0; k < kDirs; ++k) dcode[(size_t)row * kDirs + k] = out[k];
 }
 
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
-                            double2 *, int, int, double, double, int, double *, unsigned *, double *, const PairWalk);
+                            double2 *, int, int, double, double, double, int, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag, bool t2) {
-    if (t2) return diag ? cheb_pair_step<true, NW, S, MINB, 1> : cheb_pair_step<false, NW, S, MINB, 1>;
-    return diag ? cheb_pair_step<true, NW, S, MINB, 0> : cheb_pair_step<false, NW, S, MINB, 0>;
+template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag, bool self, bool t2) {
+    if (self) {
+        if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1> : cheb_pair_step<false, true, NW, S, MINB, 1>;
+        return diag ? cheb_pair_step<true, true, NW, S, MINB, 0> : cheb_pair_step<false, true, NW, S, MINB, 0>;
+    }
+    if (t2) return diag ? cheb_pair_step<true, false, NW, S, MINB, 1> : cheb_pair_step<false, false, NW, S, MINB, 1>;
+    return diag ? cheb_pair_step<true, false, NW, S, MINB, 0> : cheb_pair_step<false, false, NW, S, MINB, 0>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -466,24 +558,32 @@ struct PairShape {
     size_t smem;
 };
 
-PairShape pair_shape(bool diag, bool t2) {
+PairShape pair_shape(bool diag, bool self, bool t2) {
     PairShape s;
     // 8 warps x 2 sites: two CTAs per SM, one computes while the other waits at its barrier.  The shape
     // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
     // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
     if (env_int("BDG_PAIR_WARPS", 8) <= 8)
-        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, t2);
+        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2);
     else
-        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, t2);
+        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2);
     const int W = s.warps * s.sites;
     s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * kRingN;
     return s;
 }
 
+// On-site fragments per row straight from the table (SELF) when the dictionary is large: then the on-site blocks
+// differ from site to site (disorder, a self-consistent gap, a phase winding) and holding them in registers from
+// plane to plane would reload them on every row through the slow path.
+bool pair_self(const EllDev &e) {
+    const int forced = env_int("BDG_PAIR_SELF", -1);
+    return forced >= 0 ? forced != 0 : e.n_unique > 64;
+}
+
 }  // namespace
 
-// Does the current fixed-width copy qualify?  (dictionary built, one-dimensional x-planes, nearest-
-// neighbour stencil without wrap-around, rows of <= 5 blocks)
+// Does the current fixed-width copy qualify?  (dictionary built, one-dimensional x-planes of >= 3 sites, >= 3
+// planes, nearest-neighbour stencil -- open or periodic --, rows of <= 5 blocks)
 int pair_probe(bdg_system *sys) {
     EllDev &e = sys->ell;
     e.pair_usable = false;
@@ -497,7 +597,7 @@ int pair_probe(bdg_system *sys) {
     int *bad = sys->scratch_i32[2].as<int>();
     BDG_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), sys->stream));
     const int64_t n_slots = e.n_sites * e.width;
-    pair_check<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(n_slots, e.width, M, e.idx.as<int32_t>(), bad);
+    pair_check<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(n_slots, e.width, Lx, M, e.idx.as<int32_t>(), bad);
     BDG_CUDA(cudaGetLastError());
     int host = 1;
     BDG_CUDA(cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
@@ -506,7 +606,7 @@ int pair_probe(bdg_system *sys) {
     e.pair_M = M;
     if (e.pair_usable) {
         BDG_TRY(dev_alloc(sys, e.dcode, (size_t)e.n_sites * kDirs * sizeof(int32_t)));
-        pair_codes<<<(unsigned)ceil_div(e.n_sites, 256), 256, 0, sys->stream>>>((int)e.n_sites, e.width, M, e.idx.as<int32_t>(),
+        pair_codes<<<(unsigned)ceil_div(e.n_sites, 256), 256, 0, sys->stream>>>((int)e.n_sites, e.width, Lx, M, e.idx.as<int32_t>(),
                                                                               e.code.as<int32_t>(), e.dcode.as<int32_t>());
         BDG_CUDA(cudaGetLastError());
     }
@@ -517,7 +617,7 @@ int pair_probe(bdg_system *sys) {
 int pair_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, st.t2);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), st.t2);
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
@@ -557,12 +657,12 @@ int pair_configure(bdg_system *sys) {
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, false);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), false);
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev),
         static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1), static_cast<double2 *>(x_next2),
-        (int)e.n_sites, st.n_panels, 2.0 / st.scale, 0.0, 0, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step,
+        (int)e.n_sites, st.n_panels, 2.0 / st.scale, 0.0, 0.0, 0, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step,
         st.pair_walk);
     BDG_CUDA(cudaGetLastError());
     return BDG_OK;
@@ -572,12 +672,12 @@ int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_
 int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, true);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), true);
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_io),
         static_cast<const double2 *>(x_cur), nullptr, static_cast<double2 *>(x_io), (int)e.n_sites, st.n_panels,
-        1.0 / st.scale, (first ? 2.0 : 4.0) / st.scale, first ? 1 : 0, st.partials.as<double>(), st.tickets.as<unsigned>(),
+        1.0 / st.scale, (first ? 2.0 : 4.0) / st.scale, first ? 1.0 : 2.0, first ? 1 : 0, st.partials.as<double>(), st.tickets.as<unsigned>(),
         dots_step, st.pair_walk);
     BDG_CUDA(cudaGetLastError());
     return BDG_OK;

@@ -17,6 +17,44 @@ from util import rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
+def _periodic(api, shape, *, x=True, y=True, random_hop=False, seed=3, disorder=False):
+    """README-type s-wave system on a 2-D lattice with the reference's periodic edges filled in
+    (bodge/lattice.py:161-197; tests/test_hamiltonian.py:17-57 fills them with random matrices): wrap-around
+    bonds along x and / or the in-plane axis.  ``random_hop``: one of three random complex 2x2 matrices per bond
+    (``H[j,i] = H[i,j]^†``), else ``-t σ0`` (real-diagonal blocks: the DFMA variant).  ``disorder``: random on-site
+    potential and gap, so that every on-site block is distinct (the SELF path of the kernel)."""
+    rng = np.random.default_rng(seed)
+    lattice = api.CubicLattice(shape)
+    system = api.Hamiltonian(lattice)
+    in_plane = 1 if shape[2] == 1 else 2
+
+    pool = [-1.0 * api.σ0 + 0.3 * (rng.random((2, 2)) - 0.5 + 1j * (rng.random((2, 2)) - 0.5)) for _ in range(3)]
+
+    def hop():  # a few distinct complex matrices, so that the block dictionary still applies
+        return pool[int(rng.integers(3))] if random_hop else -1.0 * api.σ0
+
+    with system as (H, D):
+        for i in lattice.sites():
+            mu, ds = (3.0 + 0.4 * rng.random(), 0.1 + 0.2 * rng.random()) if disorder else (3.0, 0.2)
+            H[i, i] = mu * api.σ0 - 0.05 * api.σ3
+            D[i, i] = -ds * api.jσ2
+        pairs = list(lattice.bonds())
+        if x:
+            pairs += list(lattice.edges(axis=0))
+        if y:
+            pairs += list(lattice.edges(axis=in_plane))
+        done = set()
+        for i, j in pairs:
+            if (i, j) in done:
+                continue
+            h = hop()
+            H[i, j] = h
+            H[j, i] = h.conj().T
+            done.add((i, j))
+            done.add((j, i))
+    return system
+
+
 SYSTEMS = {
     # tag: (builder, hopping blocks real-diagonal -> the pair kernel runs its DFMA variant)
     "readme_24_16_1": (lambda api: cases.readme_swave(api, (24, 16, 1)), True),
@@ -24,6 +62,14 @@ SYSTEMS = {
     "junction_9_1_67": (lambda api: cases.junction(api, (9, 1, 67)), True),        # planes along z, three patches
     "dwave_13_35_1": (lambda api: cases.dwave_rashba(api, (13, 35, 1)), False),    # complex hopping + bond pairing: DMMA rows
     "readme_3_3_1": (lambda api: cases.readme_swave(api, (3, 3, 1)), True),        # smallest lattice it accepts
+    # the reference's PERIODIC skeleton with the edges filled in: the halo of the rim patches / segments is the opposite face
+    "torus_11_17_1": (lambda api: _periodic(api, (11, 17, 1)), True),
+    "torus_x_only_9_31_1": (lambda api: _periodic(api, (9, 31, 1), y=False), True),
+    "torus_y_only_5_1_23": (lambda api: _periodic(api, (5, 1, 23), x=False), True),
+    "torus_3_3_1": (lambda api: _periodic(api, (3, 3, 1)), True),                  # every site neighbours every plane
+    "torus_random_hop_7_19_1": (lambda api: _periodic(api, (7, 19, 1), random_hop=True), False),
+    "torus_disordered_10_16_1": (lambda api: _periodic(api, (10, 16, 1), disorder=True), True),   # > 64 distinct blocks: SELF path
+    "open_disordered_12_33_1": (lambda api: _periodic(api, (12, 33, 1), x=False, y=False, disorder=True, random_hop=True), False),
 }
 
 # (BDG_PAIR_SEG, BDG_PAIR_P, BDG_PAIR_WARPS): None = planner's choice
@@ -123,18 +169,22 @@ def test_pair_declines_what_it_cannot_do(gpu_api):
     assert big._sys.cheb_format()["kernel"] == "pair"
     del big
     flat = cases.readme_swave(gpu_api, (12, 12, 1))
-    # wrap-around hopping along y on an otherwise qualifying lattice
+    # wrap-around hopping along y: the torus geometry takes it (round 1 declined it)
     lattice = flat.lattice
     with flat as (H, D):
         for x in range(12):
             H[(x, 0, 0), (x, 11, 0)] = -1.0 * gpu_api.σ0
             H[(x, 11, 0), (x, 0, 0)] = -1.0 * gpu_api.σ0
-    with pytest.raises(ValueError):
-        flat._sys.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
-    got = flat.chebyshev_moments(16, vectors=8, seed=2, kernel="auto")   # ... and auto still works on it
     H2 = flat.matrix("bsr")
-    assert rel_err(got, orc.cheb_moments(H2, orc.rademacher(2, H2.shape[0], np.arange(8)), 16, flat.spectral_bound())) <= TOL
+    want = orc.cheb_moments(H2, orc.rademacher(2, H2.shape[0], np.arange(8)), 16, flat.spectral_bound())
+    for kernel in ("pair", "t2", "auto"):
+        got = flat.chebyshev_moments(16, vectors=8, seed=2, kernel=kernel)
+        assert flat._sys.cheb_format()["kernel"] == ("t2" if kernel == "auto" else kernel)
+        assert rel_err(got, want) <= TOL
     assert lattice.size == 144
+    short = cases.readme_swave(gpu_api, (2, 9, 1))              # fewer than 3 planes: x-1 and x+1 would be the same site
+    with pytest.raises(ValueError):
+        short._sys.cheb_begin(n_random=8, seed=1, scale=scale, kernel="pair")
 
 
 def test_auto_prefers_pair_where_it_is_faster(gpu_api, monkeypatch):
