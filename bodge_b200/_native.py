@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbdg.so")
+LIB_PATH = os.environ.get("BDG_LIB") or os.path.join(_PKG, "libbdg.so")  # BDG_LIB: a development build of kernel variants
 
 OK, E_INVALID, E_CUDA, E_NOT_NEIGHBOUR, E_NOT_HERMITIAN, E_OUT_OF_BOUNDS, E_NO_DEVICE = range(7)
 X0_PROBE, X0_RADEMACHER = 0, 1

@@ -33,22 +33,27 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """``defines`` / ``out``: development builds of kernel variants (``-DNAME``) into another file, loaded by
+    setting ``BDG_LIB`` (``_native.load``); the product is always ``libbdg.so`` without defines."""
+    target = out or LIB
+    if not force and not defines and not is_stale():
         return LIB
     cmd = [
         nvcc_path(), "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+        "-o", target,
+    ] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -189,5 +189,6 @@ int pair_probe(bdg_system *sys);      // sets sys->ell.pair_usable / pair_M (cal
 int pair_configure(bdg_system *sys);  // patch / segment plan and grid for the current ChebState
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step);
 int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
+bool pair_streams_onsite(const bdg_system *sys);  // on-site fragments fetched per row (large dictionaries) instead of held
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -788,8 +788,8 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     if (kernel) *kernel = st.t2 ? BDG_KERNEL_T2 : st.pair ? BDG_KERNEL_PAIR : st.kernel;
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
-        if (st.pair || st.t2)  // one pass over the codes and indices serves two steps
-            *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + e.n_unique * 256;
+        if (st.pair || st.t2)  // one pass over the codes (and, site-dependent on-site blocks: over those) serves two steps
+            *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + (pair_streams_onsite(sys) ? std::min(e.n_unique, e.n_sites) * 256 / 2 : e.n_unique * 256);
         else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_ELL)

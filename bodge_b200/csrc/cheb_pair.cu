@@ -389,12 +389,16 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
                 // Only owned rows have a [B]; the rim warps of a patch (and of a ragged last patch) own one site or none.
                 // Specialised on which of the warp's sites are live so that two live sites stay interleaved.
-                auto sub_b = [&](auto live0, auto live1) {
+                auto sub_b = [&](auto live0, auto live1, auto guard_) {
                     constexpr bool live[2] = {decltype(live0)::value, decltype(live1)::value};
+                    constexpr bool guard = decltype(guard_)::value;  // both rows computed, stores and dot products predicated
                     double2 c_[S + 2], m[S], q[S];
 #pragma unroll
-                    for (int k = 0; k < S + 2; ++k)
-                        if ((k >= 1 && live[k - 1]) || (k < S && live[k]) || (k >= 2 && live[k - 2])) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
+                    for (int k = 0; k < S + 2; ++k) {  // c_[k]: own record of site k - 1, lower neighbour of site k, upper one of site k - 2
+                        const bool need = (k >= 1 && k <= S && live[k >= 1 && k <= S ? k - 1 : 0]) || (k < S && live[k < S ? k : 0]) ||
+                                          (k >= 2 && live[k >= 2 ? k - 2 : 0]);
+                        if (need) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
+                    }
 #pragma unroll
                     for (int s = 0; s < S; ++s)
                         if (live[s]) m[s] = lds_rec(tm + (uint32_t)s * R);
@@ -414,20 +418,27 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                             const double2 sub = make_double2(fma(csub, t.x, pv[s].x), fma(csub, t.y, pv[s].y));
                             out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
                         }
-                        pout2[32 * s] = out;
-                        if (MODE == 0) {
-                            d2 = fma(c_[1 + s].x, c_[1 + s].x, fma(c_[1 + s].y, c_[1 + s].y, d2));
-                        } else {
-                            d2 = fma(out.x, t.x, fma(out.y, t.y, d2));
+                        if (!guard || owned[s]) {
+                            pout2[32 * s] = out;
+                            if (MODE == 0) {
+                                d2 = fma(c_[1 + s].x, c_[1 + s].x, fma(c_[1 + s].y, c_[1 + s].y, d2));
+                            } else {
+                                d2 = fma(out.x, t.x, fma(out.y, t.y, d2));
+                            }
+                            d3 = fma(out.x, c_[1 + s].x, fma(out.y, c_[1 + s].y, d3));
                         }
-                        d3 = fma(out.x, c_[1 + s].x, fma(out.y, c_[1 + s].y, d3));
                     }
                 };
                 static_assert(S == 2, "sub_b is specialised for two sites per warp");
+#ifdef BDG_PAIR_NOSPEC
+                hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
+                sub_b(std::true_type{}, std::true_type{}, std::true_type{});
+#else
                 if (owned[0] || owned[1]) hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
-                if (owned[0] && owned[1]) sub_b(std::true_type{}, std::true_type{});
-                else if (owned[0]) sub_b(std::true_type{}, std::false_type{});
-                else if (owned[1]) sub_b(std::false_type{}, std::true_type{});
+                if (owned[0] && owned[1]) sub_b(std::true_type{}, std::true_type{}, std::false_type{});
+                else if (owned[0]) sub_b(std::true_type{}, std::false_type{}, std::false_type{});
+                else if (owned[1]) sub_b(std::false_type{}, std::true_type{}, std::false_type{});
+#endif
             }
             if (MODE == 1 && store && !first) {  // E_{j-1} of this plane: [B] of the next iteration works on it (and overwrites it)
 #pragma unroll
@@ -581,6 +592,8 @@ bool pair_self(const EllDev &e) {
 }
 
 }  // namespace
+
+bool pair_streams_onsite(const bdg_system *sys) { return pair_self(sys->ell); }
 
 // Does the current fixed-width copy qualify?  (dictionary built, one-dimensional x-planes of >= 3 sites, >= 3
 // planes, nearest-neighbour stencil -- open or periodic --, rows of <= 5 blocks)
