@@ -11,11 +11,16 @@ from .hamiltonian import *
 from .helpers import *
 from .lattice import *
 
-__version__ = "0.1.0"
+from ._native import release_cached
+from .hamiltonian import AccuracyWarning
+
+__version__ = "0.2.0"
 __all__ = [
     "Lattice", "CubicLattice", "Hamiltonian", "Coord", "Coords", "Index", "Indices",
     "ssd", "swave", "pwave", "dwave",
     "π", "σ", "σ0", "σ1", "σ2", "σ3", "jσ", "jσ0", "jσ1", "jσ2", "jσ3",
     "pi", "sigma", "sigma0", "sigma1", "sigma2", "sigma3",
     "jsigma", "jsigma0", "jsigma1", "jsigma2", "jsigma3",
+    # additions of this implementation
+    "AccuracyWarning", "release_cached",
 ]

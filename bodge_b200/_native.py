@@ -89,6 +89,29 @@ def load():
     return lib
 
 
+_pack = None
+
+
+def pack_dict(entries: dict, keys: np.ndarray, vals: np.ndarray) -> int:
+    """Write the ``((x,y,z),(x,y,z)) -> 2x2 complex128`` entries of a dict into ``keys [n,2,3] int64`` and
+    ``vals [n,2,2] complex128`` with one C loop (``csrc/pack_dict.c``).  Returns the number of entries written,
+    or a negative number if an entry is not of that plain form (the caller packs the dict with numpy instead);
+    -1 also when the helper library has not been built (it is optional: a speed-up, not a code path of its own)."""
+    global _pack
+    if _pack is None:
+        path = os.path.join(_PKG, "_bdgpack.so")
+        if not os.path.exists(path):
+            _pack = False
+        else:
+            lib = C.PyDLL(path)
+            lib.bdg_pack_dict.argtypes = [C.py_object, _vp, _vp]
+            lib.bdg_pack_dict.restype = C.c_longlong
+            _pack = lib
+    if _pack is False:
+        return -1
+    return int(_pack.bdg_pack_dict(entries, keys.ctypes.data_as(_vp), vals.ctypes.data_as(_vp)))
+
+
 def last_error() -> str:
     return load().bdg_last_error().decode("utf-8", "replace")
 
@@ -121,6 +144,18 @@ def device_count() -> int:
 
 def _ptr(a: np.ndarray | None):
     return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _as_index(a, what="site index"):
+    """int32 site indices for the ABI; wider integers are range-checked (no silent wrap), floats refused."""
+    a = np.asarray(a)
+    if a.dtype == np.int32:
+        return np.ascontiguousarray(a)
+    if a.size and a.dtype.kind not in "iu":
+        raise TypeError(f"{what} arrays must be integers, got {a.dtype}")
+    if a.size and (int(a.min()) < np.iinfo(np.int32).min or int(a.max()) > np.iinfo(np.int32).max):
+        raise ValueError(f"{what} out of the int32 range of the BSR structure")
+    return np.ascontiguousarray(a, dtype=np.int32)
 
 
 def _as(a, dtype, shape_tail=()):
@@ -156,7 +191,7 @@ class System:
     @classmethod
     def generic(cls, n_sites, pair_i, pair_j, device=0):
         lib = load()
-        pi, pj = _as(pair_i, np.int32), _as(pair_j, np.int32)
+        pi, pj = _as_index(pair_i), _as_index(pair_j)
         h = _vp()
         check(lib.bdg_create_generic(device, int(n_sites), len(pi), _ptr(pi), _ptr(pj), C.byref(h)))
         return cls._finish(lib, h, device)
@@ -192,15 +227,15 @@ class System:
 
     # -- assembly -----------------------------------------------------------------------------
     def lookup(self, i, j) -> np.ndarray:
-        i, j = _as(i, np.int32), _as(j, np.int32)
+        i, j = _as_index(i), _as_index(j)
         k = np.empty(len(i), dtype=np.int64)
         bad = C.c_int64(-1)
         check(load().bdg_lookup(self._h, len(i), _ptr(i), _ptr(j), _ptr(k), C.byref(bad)))
         return k
 
     def scatter(self, h_i, h_j, h_val, p_i, p_j, p_val, herm_tol=1e-6) -> float:
-        h_i, h_j = _as(h_i, np.int32), _as(h_j, np.int32)
-        p_i, p_j = _as(p_i, np.int32), _as(p_j, np.int32)
+        h_i, h_j = _as_index(h_i), _as_index(h_j)
+        p_i, p_j = _as_index(p_i), _as_index(p_j)
         h_val = _as(np.asarray(h_val).reshape(-1, 2, 2), np.complex128, (2, 2))
         p_val = _as(np.asarray(p_val).reshape(-1, 2, 2), np.complex128, (2, 2))
         if not (len(h_i) == len(h_j) == len(h_val) and len(p_i) == len(p_j) == len(p_val)):

@@ -15,6 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbdg.so")
+PACK = os.path.join(PKG, "_bdgpack.so")  # host-side dict packer (CPython API, no CUDA): csrc/pack_dict.c
 SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu", "cheb_pair.cu", "observables.cu"]
 
 
@@ -29,14 +30,29 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "bdg.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".c")] + [os.path.join(ROOT, "include", "bdg.h")]
     return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build_packer(force: bool = False) -> str:
+    """gcc -shared csrc/pack_dict.c -> _bdgpack.so (resolves the CPython symbols from the running interpreter)."""
+    import sysconfig
+
+    src = os.path.join(CSRC, "pack_dict.c")
+    if not force and os.path.exists(PACK) and os.path.getmtime(PACK) >= os.path.getmtime(src):
+        return PACK
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler found for csrc/pack_dict.c")
+    subprocess.run([cc, "-O2", "-Wall", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", PACK, src], check=True)
+    return PACK
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
     """``defines`` / ``out``: development builds of kernel variants (``-DNAME``) into another file, loaded by
     setting ``BDG_LIB`` (``_native.load``); the product is always ``libbdg.so`` without defines."""
     target = out or LIB
+    build_packer(force)
     if not force and not defines and not is_stale():
         return LIB
     cmd = [

@@ -99,7 +99,8 @@ void dev_free(bdg_system *sys, DevBuf &buf) {
         bool cached = false;
         if (buf.bytes >= kCacheMinBytes) {
             // cudaFree would wait for the device; a recycled buffer must at least not be in use on this stream
-            cudaStreamSynchronize(sys->stream);
+            // (a handle being destroyed has synchronised once already: bdg_destroy)
+            if (!sys->quiesced) cudaStreamSynchronize(sys->stream);
             cached = cache_put(sys->device, buf.ptr, buf.bytes);
         }
         if (!cached) cudaFree(buf.ptr);
@@ -143,19 +144,25 @@ static int create_common(int device, bdg_system **out) {
     BDG_CUDA(cudaSetDevice(device));
     bdg_system *sys = new bdg_system();
     sys->device = device;
-    BDG_CUDA(cudaDeviceGetAttribute(&sys->sm_count, cudaDevAttrMultiProcessorCount, device));  // (cudaGetDeviceProperties takes milliseconds)
-    BDG_CUDA(cudaStreamCreateWithFlags(&sys->own_stream, cudaStreamNonBlocking));
-    sys->stream = sys->own_stream;
-    int rc = dev_alloc(sys, sys->scalars, sizeof(Scalars));
-    if (rc != BDG_OK) return rc;
-    {   // pinned pages are expensive to create: recycle them like the device buffers
-        std::lock_guard<std::mutex> lock(g_cache_mutex);
-        if (!g_host_pages.empty()) {
-            sys->host_scalars = g_host_pages.back();
-            g_host_pages.pop_back();
+    int rc = [&]() -> int {
+        BDG_CUDA(cudaDeviceGetAttribute(&sys->sm_count, cudaDevAttrMultiProcessorCount, device));  // (cudaGetDeviceProperties takes milliseconds)
+        BDG_CUDA(cudaStreamCreateWithFlags(&sys->own_stream, cudaStreamNonBlocking));
+        sys->stream = sys->own_stream;
+        BDG_TRY(dev_alloc(sys, sys->scalars, sizeof(Scalars)));
+        {   // pinned pages are expensive to create: recycle them like the device buffers
+            std::lock_guard<std::mutex> lock(g_cache_mutex);
+            if (!g_host_pages.empty()) {
+                sys->host_scalars = g_host_pages.back();
+                g_host_pages.pop_back();
+            }
         }
+        if (!sys->host_scalars) BDG_CUDA(cudaMallocHost(&sys->host_scalars, sizeof(Scalars)));
+        return BDG_OK;
+    }();
+    if (rc != BDG_OK) {  // release whatever exists (bdg_destroy copes with a half-built handle)
+        bdg_destroy(sys);
+        return rc;
     }
-    if (!sys->host_scalars) BDG_CUDA(cudaMallocHost(&sys->host_scalars, sizeof(Scalars)));
     *out = sys;
     return BDG_OK;
 }
@@ -182,6 +189,8 @@ extern "C" int bdg_destroy(bdg_t *sys) {
     if (!sys) return BDG_OK;
     cudaSetDevice(sys->device);
     cudaStreamSynchronize(sys->stream);
+    if (sys->own_stream && sys->stream != sys->own_stream) cudaStreamSynchronize(sys->own_stream);
+    sys->quiesced = true;  // nothing is enqueued from here on: the buffers go back to the cache without further syncs
     cheb_release(sys);
     free_bsr(sys, sys->skel);
     free_bsr(sys, sys->packed);

@@ -148,6 +148,7 @@ struct bdg_system {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    bool quiesced = false;     // being destroyed, stream drained: dev_free need not synchronise per buffer
     int64_t dev_bytes = 0;
     int cubic[3] = {0, 0, 0};  // (Lx, Ly, Lz) when built by bdg_create_cubic, else zeros
 

@@ -660,6 +660,14 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
     BDG_REQUIRE(n_steps >= 0, "negative step count");
     BDG_TRY(ensure_dot_capacity(sys, st.steps_done + n_steps + 1));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    // (the events are destroyed on every path out, failures included)
+    struct Events {
+        cudaEvent_t &a, &b;
+        ~Events() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } events{e0, e1};
     if (elapsed_ms) {
         BDG_CUDA(cudaEventCreate(&e0));
         BDG_CUDA(cudaEventCreate(&e1));
@@ -690,8 +698,6 @@ extern "C" int bdg_cheb_steps(bdg_t *sys, int32_t n_steps, float *elapsed_ms) {
         BDG_CUDA(cudaEventRecord(e1, sys->stream));
         BDG_CUDA(cudaEventSynchronize(e1));
         BDG_CUDA(cudaEventElapsedTime(elapsed_ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
     return BDG_OK;
 }

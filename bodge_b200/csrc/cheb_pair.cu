@@ -138,36 +138,46 @@ __device__ __forceinline__ void self_fragments(int jv, double (&f)[S], const dou
     }
 }
 
-// y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell
-// (directions: self, x-1, y-1, y+1, x+1 = ascending block column).
+// y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell (directions: self, x-1, y-1,
+// y+1, x+1 = ascending block column on an open lattice), in stages so that sub-step [B] can start on the records its
+// own warp wrote while the rest of the CTA is still arriving at the barrier: begin (self), add x 4, end.
+template <bool DIAG> struct RowSum {
+    double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0, yr = 0.0, yi = 0.0;
+    __device__ __forceinline__ void begin(const double2 &x0, double b0) {
+        dmma_8x8x4(a10, a11, x0.x, b0);
+        dmma_8x8x4(a20, a21, x0.y, b0);
+        if (DIAG) yr = a10 - a21, yi = a11 + a20;
+    }
+    __device__ __forceinline__ void add(const double2 &x, double b) {
+        if (DIAG) {
+            yr = fma(b, x.x, yr);
+            yi = fma(b, x.y, yi);
+        } else {
+            dmma_8x8x4(a10, a11, x.x, b);
+            dmma_8x8x4(a20, a21, x.y, b);
+        }
+    }
+    __device__ __forceinline__ void end() {
+        if (!DIAG) yr = a10 - a21, yi = a11 + a20;
+    }
+};
+
 template <bool DIAG>
 __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1, const double2 &x2, const double2 &x3,
                                             const double2 &x4, double b0, const double (&bop)[kDirs], double &yr, double &yi) {
-    double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
-    dmma_8x8x4(a10, a11, x0.x, b0);
-    dmma_8x8x4(a20, a21, x0.y, b0);
-    if (!DIAG) {
-        dmma_8x8x4(a10, a11, x1.x, bop[1]);
-        dmma_8x8x4(a20, a21, x1.y, bop[1]);
-        dmma_8x8x4(a10, a11, x2.x, bop[2]);
-        dmma_8x8x4(a20, a21, x2.y, bop[2]);
-        dmma_8x8x4(a10, a11, x3.x, bop[3]);
-        dmma_8x8x4(a20, a21, x3.y, bop[3]);
-        dmma_8x8x4(a10, a11, x4.x, bop[4]);
-        dmma_8x8x4(a20, a21, x4.y, bop[4]);
-    }
-    yr = a10 - a21;
-    yi = a11 + a20;
-    if (DIAG) {
-        yr = fma(bop[1], x1.x, yr);
-        yi = fma(bop[1], x1.y, yi);
-        yr = fma(bop[2], x2.x, yr);
-        yi = fma(bop[2], x2.y, yi);
-        yr = fma(bop[3], x3.x, yr);
-        yi = fma(bop[3], x3.y, yi);
-        yr = fma(bop[4], x4.x, yr);
-        yi = fma(bop[4], x4.y, yi);
-    }
+    RowSum<DIAG> r;
+    r.begin(x0, b0);
+    r.add(x1, bop[1]);
+    r.add(x2, bop[2]);
+    r.add(x3, bop[3]);
+    r.add(x4, bop[4]);
+    r.end();
+    yr = r.yr;
+    yi = r.yi;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 
 // NW warps per CTA, two ADJACENT sites per warp and plane: W = 2 NW sites per plane in sub-step [A]
@@ -226,11 +236,13 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int r = 0; r < kRingN; ++r) mbar_init(sBar + 8 * r, 1);
+        mbar_init(sBar + 8 * kRingN, NW * 32);  // [A] -> [B] hand-over: every thread arrives, waits later (split phase)
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
     __syncthreads();
     uint32_t cnt = 0;  // T_n planes consumed by the items before this one
+    uint32_t xphase = 0;  // parity of the hand-over barrier's current phase (one phase per iteration)
     const size_t gstep = (size_t)wk.M * 32;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 
@@ -313,7 +325,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         double2 *pout1 = tc + gbase;                            // MODE 0: T_{n+1}(plane of [A])
         double2 *pout2 = td + gbase - (ptrdiff_t)gstep;         // T_{n+2} / E_{j+1}(plane of [B]) = one plane behind [A]
         // MODE 0: T_{n-1} of ALL rows [A] computes (halo rows and halo planes included), wrapped like the codes;
-        // MODE 1: E_{j-1} of the owned rows of the plane [B] works on, loaded right after the previous [B] used the registers.
+        // MODE 1: E_{j-1} of the owned rows of the plane [B] works on.  Both one plane ahead (pvn).
         int yw[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -322,17 +334,51 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         }
         int xprev = x0 - 1;  // wrapped plane of [A]
         xprev += xprev < 0 ? wk.Lx : 0;
-        double2 pv[S];
+        double2 pv[S], pvn[S];  // MODE 1: E_{j-1} of the plane of [B] in this / in the next iteration
+#ifdef BDG_PAIR_PV3
+        double2 pvn2[S];        // ... and in the one after: the load is issued two and a half iterations ahead of its use
+#pragma unroll
+        for (int s = 0; s < S; ++s) pvn2[s] = make_double2(0.0, 0.0);
+#endif
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pv[s] = make_double2(0.0, 0.0);
-            if (MODE == 0) pv[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
+            pv[s] = pvn[s] = make_double2(0.0, 0.0);
+            if (MODE == 0) pvn[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
         }
         wait(0);
         wait(1);
 
         for (int i = 0; i <= len + 1; ++i, pin_ += gstep, pout1 += gstep, pout2 += gstep) {
             const bool store = i >= 1 && i <= len;
+            if (MODE == 1) {
+                // E_{j-1} of the plane of [A]: [B] of the NEXT iteration works on that plane (and overwrites it) -- issued
+                // here, an iteration and a half ahead of its use (half an iteration does not cover the HBM latency: measured)
+#ifdef BDG_PAIR_PV3
+                const bool store_next = i + 1 <= len;  // the plane of [A] in the next iteration is an owned plane
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    pv[s] = pvn[s];
+                    pvn[s] = pvn2[s];
+                    if (store_next && owned[s] && !first) pvn2[s] = ld_prev_rw(pin_ + gstep + 32 * s);
+                }
+#else
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    pv[s] = pvn[s];
+                    if (store && owned[s] && !first) pvn[s] = ld_prev_rw(pin_ + 32 * s);
+                }
+#endif
+            } else {  // T_{n-1} of the next plane of [A], one iteration ahead
+                if (i <= len) {
+                    xprev += 1;
+                    xprev -= xprev >= wk.Lx ? wk.Lx : 0;
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    pv[s] = pvn[s];
+                    if (i <= len) pvn[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
+                }
+            }
             wait(i + 2);
             int jnext = -1;
             cplane += plane_codes;
@@ -340,6 +386,26 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             if (code_lane && i <= len) jnext = __ldg(dcode + cplane + coff);
             if (SELF) self_fragments<S>(jnext, fsN, table, lane);
             double2 tn[S];  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
+            // [B]: update, store and dot products of row s from its product (yr, yi) and its own T_{n+1} record
+            auto finish_b = [&](int s, double yr, double yi, const double2 &own1) {
+                const double2 t = tn[s];
+                double2 out;
+                if (MODE == 0) {
+                    out = make_double2(fma(alpha, yr, -t.x), fma(alpha, yi, -t.y));
+                } else {
+                    const double2 sub = make_double2(fma(csub, t.x, pv[s].x), fma(csub, t.y, pv[s].y));
+                    out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
+                }
+                if (owned[s]) {
+                    pout2[32 * s] = out;
+                    if (MODE == 0) {
+                        d2 = fma(own1.x, own1.x, fma(own1.y, own1.y, d2));
+                    } else {
+                        d2 = fma(out.x, t.x, fma(out.y, t.y, d2));
+                    }
+                    d3 = fma(out.x, own1.x, fma(out.y, own1.y, d3));
+                }
+            };
             {
                 const uint32_t c = cnt + (uint32_t)i;
                 const uint32_t nm = aN + (c & (kRingN - 1)) * PLANE_N;
@@ -372,13 +438,8 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                         }
                     }
                 }
-                if (MODE == 0 && i <= len) {  // T_{n-1} of the next plane of [A]
-                    xprev += 1;
-                    xprev -= xprev >= wk.Lx ? wk.Lx : 0;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) pv[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
-                }
             }
+#ifndef BDG_PAIR_SPLIT
             __syncthreads();  // T_{n+1} of this plane complete in the ring
             // ... and [A] is done in every warp: plane i (its x-1 neighbours) is dead, its slot takes plane i + 8 -- seven
             // planes in flight beyond the one in use.
@@ -387,64 +448,64 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
                 const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
-                // Only owned rows have a [B]; the rim warps of a patch (and of a ragged last patch) own one site or none.
-                // Specialised on which of the warp's sites are live so that two live sites stay interleaved.
-                auto sub_b = [&](auto live0, auto live1, auto guard_) {
-                    constexpr bool live[2] = {decltype(live0)::value, decltype(live1)::value};
-                    constexpr bool guard = decltype(guard_)::value;  // both rows computed, stores and dot products predicated
-                    double2 c_[S + 2], m[S], q[S];
-#pragma unroll
-                    for (int k = 0; k < S + 2; ++k) {  // c_[k]: own record of site k - 1, lower neighbour of site k, upper one of site k - 2
-                        const bool need = (k >= 1 && k <= S && live[k >= 1 && k <= S ? k - 1 : 0]) || (k < S && live[k < S ? k : 0]) ||
-                                          (k >= 2 && live[k >= 2 ? k - 2 : 0]);
-                        if (need) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
-                    }
-#pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        if (live[s]) m[s] = lds_rec(tm + (uint32_t)s * R);
-#pragma unroll
-                    for (int s = 0; s < S; ++s)
-                        if (live[s]) q[s] = lds_rec(tp + (uint32_t)s * R);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        if (!live[s]) continue;
-                        double yr, yi;
-                        row_product<DIAG>(c_[1 + s], m[s], c_[s], c_[2 + s], q[s], SELF ? fsB[s] : keep[s][0], keep[s], yr, yi);
-                        const double2 t = tn[s];
-                        double2 out;
-                        if (MODE == 0) {
-                            out = make_double2(fma(alpha, yr, -t.x), fma(alpha, yi, -t.y));
-                        } else {
-                            const double2 sub = make_double2(fma(csub, t.x, pv[s].x), fma(csub, t.y, pv[s].y));
-                            out = make_double2(fma(alpha2, yr, -sub.x), fma(alpha2, yi, -sub.y));
-                        }
-                        if (!guard || owned[s]) {
-                            pout2[32 * s] = out;
-                            if (MODE == 0) {
-                                d2 = fma(c_[1 + s].x, c_[1 + s].x, fma(c_[1 + s].y, c_[1 + s].y, d2));
-                            } else {
-                                d2 = fma(out.x, t.x, fma(out.y, t.y, d2));
-                            }
-                            d3 = fma(out.x, c_[1 + s].x, fma(out.y, c_[1 + s].y, d3));
-                        }
-                    }
-                };
-                static_assert(S == 2, "sub_b is specialised for two sites per warp");
-#ifdef BDG_PAIR_NOSPEC
                 hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
-                sub_b(std::true_type{}, std::true_type{}, std::true_type{});
-#else
-                if (owned[0] || owned[1]) hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
-                if (owned[0] && owned[1]) sub_b(std::true_type{}, std::true_type{}, std::false_type{});
-                else if (owned[0]) sub_b(std::true_type{}, std::false_type{}, std::false_type{});
-                else if (owned[1]) sub_b(std::false_type{}, std::true_type{}, std::false_type{});
-#endif
-            }
-            if (MODE == 1 && store && !first) {  // E_{j-1} of this plane: [B] of the next iteration works on it (and overwrites it)
+                double2 c_[S + 2], m[S], q[S];
 #pragma unroll
-                for (int s = 0; s < S; ++s)
-                    if (owned[s]) pv[s] = ld_prev_rw(pin_ + 32 * s);
+                for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double yr, yi;
+                    row_product<DIAG>(c_[1 + s], m[s], c_[s], c_[2 + s], q[s], SELF ? fsB[s] : keep[s][0], keep[s], yr, yi);
+                    finish_b(s, yr, yi, c_[1 + s]);
+                }
             }
+#else
+            // Split-phase hand-over: arrive, start [B] on the T_{n+1} records this warp wrote itself (own sites of the
+            // three planes: the on-site product, the x-1 term, and for the upper site its lower neighbour), and only then
+            // wait for the other warps' records (one neighbour below, one above).  The order of the terms of a row is
+            // unchanged (self, x-1, y-1, y+1, x+1).
+            static_assert(S == 2, "the staged [B] is written for two sites per warp");
+            mbar_arrive(sBar + 8 * kRingN);
+            if (i >= 2) {
+                const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
+                const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
+                const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
+                hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
+                double2 own[S], m[S], q[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) own[s] = lds_rec(t0 + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+#pragma unroll
+                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                RowSum<DIAG> r0, r1;
+                r0.begin(own[0], SELF ? fsB[0] : keep[0][0]);
+                r1.begin(own[1], SELF ? fsB[1] : keep[1][0]);
+                r0.add(m[0], keep[0][1]);
+                r1.add(m[1], keep[1][1]);
+                r1.add(own[0], keep[1][2]);
+                mbar_wait(sBar + 8 * kRingN, xphase);
+                issue(i + kRingN);
+                const double2 lo = lds_rec(t0 - R), hi = lds_rec(t0 + 2 * R);
+                r0.add(lo, keep[0][2]);
+                r0.add(own[1], keep[0][3]);
+                r1.add(hi, keep[1][3]);
+                r0.add(q[0], keep[0][4]);
+                r1.add(q[1], keep[1][4]);
+                r0.end();
+                r1.end();
+                finish_b(0, r0.yr, r0.yi, own[0]);
+                finish_b(1, r1.yr, r1.yi, own[1]);
+            } else {
+                mbar_wait(sBar + 8 * kRingN, xphase);
+                issue(i + kRingN);
+            }
+            xphase ^= 1u;
+#endif
             jvB = jvA;
             jvA = jnext;
 #pragma unroll
@@ -579,7 +640,7 @@ PairShape pair_shape(bool diag, bool self, bool t2) {
     else
         s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2);
     const int W = s.warps * s.sites;
-    s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * kRingN;
+    s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * (kRingN + 1);
     return s;
 }
 

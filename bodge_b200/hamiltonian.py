@@ -14,10 +14,37 @@ the built library) raises ``RuntimeError``.
 from __future__ import annotations
 
 import os
+import warnings
 
 from . import _native, distributed, kpm
 from .common import *
+from .helpers import dwave, pwave, ssd, swave  # the reference exports them from bodge.hamiltonian (hamiltonian.py:390-531)
 from .lattice import CubicLattice, Lattice
+
+
+class AccuracyWarning(UserWarning):
+    """A KPM observable was asked for (or capped at) fewer Chebyshev moments than its tolerance needs."""
+
+
+class _DeviceData(np.ndarray):
+    """Host snapshot of the device-resident ``data`` array that WRITES THROUGH: the reference hands out the live
+    array (``system._data``, advertised by ``index()``'s docstring: ``system._data[k, ...] = v``), so item assignment
+    on this view -- or on any slice of it -- uploads the edited snapshot to the GPU."""
+
+    def __new__(cls, array, owner):
+        obj = np.asarray(array).view(cls)
+        obj._owner, obj._root = owner, obj
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+        self._root = getattr(obj, "_root", None)
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        if self._owner is not None and self._root is not None:
+            self._owner._scale_cache = None
+            self._owner._sys.import_data(np.asarray(self._root))
 
 
 def _default_device() -> int:
@@ -34,21 +61,27 @@ def _pack_entries(lattice: Lattice, entries: dict):
     if n == 0:
         none = np.zeros(0, dtype=np.int64)
         return none, none.copy(), np.zeros((0, 2, 2), dtype=np.complex128)
-    try:
-        keys = np.array(list(entries.keys()), dtype=np.int64)
-    except (ValueError, TypeError, OverflowError) as err:
-        raise TypeError("Hamiltonian keys must be pairs of integer (x, y, z) coordinates") from err
-    if keys.shape != (n, 2, 3):
-        raise TypeError("Hamiltonian keys must be pairs of integer (x, y, z) coordinates")
+    # Fast path: one C loop over the dict (csrc/pack_dict.c) when every entry has the plain form the reference's
+    # own examples use -- integer coordinate tuples and 2x2 complex128 arrays.
+    keys = np.empty((n, 2, 3), dtype=np.int64)
+    vals = np.empty((n, 2, 2), dtype=np.complex128)
+    if _native.pack_dict(entries, keys, vals) != n:
+        try:
+            keys = np.array(list(entries.keys()))
+        except (ValueError, TypeError, OverflowError) as err:
+            raise TypeError("Hamiltonian keys must be pairs of integer (x, y, z) coordinates") from err
+        if keys.shape != (n, 2, 3) or keys.dtype.kind not in "iu":
+            raise TypeError("Hamiltonian keys must be pairs of integer (x, y, z) coordinates")
+        keys = keys.astype(np.int64)
+        try:
+            vals = np.array(list(entries.values()), dtype=np.complex128)
+            if vals.shape != (n, 2, 2):
+                raise ValueError
+        except ValueError:
+            # Mixed shapes: the reference assigns with numpy broadcasting (hamiltonian.py:107-118).
+            vals = np.stack([np.broadcast_to(np.asarray(v, dtype=np.complex128), (2, 2)) for v in entries.values()])
     i = lattice.index_many(keys[:, 0, :])
     j = lattice.index_many(keys[:, 1, :])
-    try:
-        vals = np.array(list(entries.values()), dtype=np.complex128)
-        if vals.shape != (n, 2, 2):
-            raise ValueError
-    except ValueError:
-        # Mixed shapes: the reference assigns with numpy broadcasting (hamiltonian.py:107-118).
-        vals = np.stack([np.broadcast_to(np.asarray(v, dtype=np.complex128), (2, 2)) for v in entries.values()])
     return i, j, vals
 
 
@@ -136,7 +169,7 @@ class Hamiltonian:
 
     @property
     def _data(self) -> Matrix:
-        return self._sys.export_bsr(False)[2]
+        return _DeviceData(self._sys.export_bsr(False)[2], self)
 
     @_data.setter
     def _data(self, value):
@@ -301,6 +334,7 @@ class Hamiltonian:
             if not torch.cuda.is_available():
                 raise RuntimeError("`cuda=True` needs a CUDA device.")
             dev = torch.device("cuda", self.device)
+            _native.release_cached(self.device)  # the library's recycled buffers go back to the driver before torch allocates
             w, v = torch.linalg.eigh(torch.as_tensor(np.asarray(H), device=dev))
             eigval, eigvec = w.cpu().numpy(), v.cpu().numpy()
             keep = np.where(eigval > 0)
@@ -317,18 +351,26 @@ class Hamiltonian:
     @typecheck
     def free_energy(self, temperature: float = 0.0, cuda: bool = False, *, moments: int | None = None,
                     vectors: int | None = None, seed: int = 1234, scale: float | None = None,
-                    kernel: str = "auto") -> float:
+                    kernel: str = "auto", tol: float = 1e-13) -> float:
         """Landau free energy ``F = U - TS`` of the BdG quasiparticles (hamiltonian.py:253-321).
 
-        ``cuda=False``: the reference's algorithm, a dense ``eigvalsh`` (LAPACK through scipy).
+        ``cuda=False``: the reference's algorithm, a dense ``eigvalsh`` (LAPACK through scipy) -- exact.
 
         ``cuda=True``: kernel-polynomial expansion on the GPU.  ``F = Tr g(H)`` with
         ``g(ε) = -(T/2) ln(1 + e^{-ε/T})`` is expanded in ``moments`` Chebyshev polynomials of
         ``H/scale``; the trace is exact (all 4N unit vectors) when ``vectors is None``, else a
-        stochastic estimate from ``vectors`` Rademacher columns.  For T > 0 the exact-trace
-        result agrees with the dense path to ~1e-12 relative once ``moments ≳ 30·scale/(πT)``
-        (the default); at T = 0 the integrand has a kink and polynomial expansion reaches only
-        ~1e-7.  Multi-GPU: columns are sharded over the initialised ``torch.distributed`` group.
+        stochastic estimate from ``vectors`` Rademacher columns.  Accuracy of the expansion (the reference's
+        ``cuda=True`` is an exact dense eigensolver, so this is the one place the two differ):
+
+        * T > 0: the series converges like ``exp(-n π T / scale)``; ``moments=None`` picks the length for a relative
+          truncation error ``tol`` (default 1e-13: 1e-12 agreement with the dense path measured at C1), capped at
+          32768 terms -- below ``T ≈ 1e-3 · scale`` the cap bites and an ``AccuracyWarning`` states the level reached;
+        * T = 0 (the API default): ``g`` has a kink at the Fermi level, the series converges only algebraically --
+          about 1e-7 relative at the default 8192 moments, 1e-4 in the worst cases -- and an ``AccuracyWarning``
+          says so; use ``cuda=False`` or a small finite T when more is needed;
+        * an explicit ``moments`` below what ``tol`` asks for warns too.
+
+        Multi-GPU: columns are sharded over the initialised ``torch.distributed`` group.
         """
         T = temperature
         if T < 0:
@@ -340,7 +382,17 @@ class Hamiltonian:
             return float(-(1 / 2) * np.sum(ε) - T * S)
 
         scale = self.spectral_bound() if scale is None else float(scale)
-        n_mom = kpm.default_moments(T, scale) if moments is None else int(moments)
+        need, reached = kpm.free_energy_moments(T, scale, tol)
+        n_mom = need if moments is None else int(moments)
+        if T == 0:
+            warnings.warn("free_energy(cuda=True) at T = 0 expands the kinked g(ε) = min(ε, 0)/2 in Chebyshev polynomials: "
+                          f"expect ~{reached * (need / max(n_mom, 1)) ** 2:.0e} relative error with {n_mom} moments (algebraic "
+                          "convergence); cuda=False is exact, a small finite T converges geometrically", AccuracyWarning, stacklevel=2)
+        elif n_mom < need or reached > tol:
+            level = max(reached, kpm.series_error(n_mom, np.pi * T / scale))
+            warnings.warn(f"free_energy(cuda=True): {n_mom} moments at T = {T:g}, scale = {scale:.3g} truncate the series at "
+                          f"~{level:.1e} relative (tol = {tol:g} needs {int(np.ceil(-np.log(tol) * scale / (np.pi * T)))})",
+                          AccuracyWarning, stacklevel=2)
         # F = sum_n c_n Tr T_n(H/scale): the series is contracted with the moments on the device,
         # so one double per GPU crosses PCIe / NVLink instead of the moment arrays.
         coef = kpm.chebyshev_coefficients(lambda e: kpm.free_energy_density(e, T), n_mom, scale)
@@ -357,17 +409,20 @@ class Hamiltonian:
 
     @typecheck
     def ldos(self, site: Coord, energies: Matrix | list[float], *, moments: int | None = None,
-             scale: float | None = None, kernel: str = "auto") -> Matrix:
+             scale: float | None = None, kernel: str = "auto", tol: float = 1e-13) -> Matrix:
         """Local density of states at ``site`` (hamiltonian.py:323-387).
 
         Same definition as the reference -- ``ρ(±ε) = -Im Σ_σ [(ε + iΓ - H)^{-1}]_{σσ} / π`` with
         ``Γ = np.gradient(unique(|ε|))`` -- but the resolvent diagonal is evaluated from the
         Chebyshev moments of the four unit vectors at ``site`` (one GPU recursion for all
-        energies) instead of one sparse LU solve per energy."""
-        return self.ldos_map([site], energies, moments=moments, scale=scale, kernel=kernel)[0]
+        energies) instead of one sparse LU solve per energy.  ``moments=None`` takes as many as the smallest
+        broadening needs for a truncation error ``tol`` (``≈ 30·scale/Γ``); fewer -- passed explicitly, or because the
+        2^20 cap bites -- raise an ``AccuracyWarning``: the truncated series oscillates and may turn negative where
+        the reference's exact solve cannot."""
+        return self.ldos_map([site], energies, moments=moments, scale=scale, kernel=kernel, tol=tol)[0]
 
     def ldos_map(self, sites, energies, *, moments: int | None = None, scale: float | None = None,
-                 kernel: str = "auto") -> Matrix:
+                 kernel: str = "auto", tol: float = 1e-13) -> Matrix:
         """LDOS at many sites: ``result[s, e]``; all ``4 * len(sites)`` probe columns run together
         (sharded over GPUs when ``torch.distributed`` is initialised)."""
         energies = np.array(energies, dtype=float)
@@ -375,9 +430,16 @@ class Hamiltonian:
         eps = np.unique(np.abs(energies))
         if eps.size < 2:
             raise ValueError("need at least two distinct |energies| to define the broadening Γ")
-        if moments is None:
-            moments = kpm.ldos_moments_needed(scale, float(np.min(np.abs(np.gradient(eps)))))
-        moments = int(moments)
+        gamma_min = float(np.min(np.abs(np.gradient(eps))))
+        need, reached = kpm.ldos_moments(scale, gamma_min, tol)
+        moments = need if moments is None else int(moments)
+        if moments < need or reached > tol:
+            # the reference's spsolve LDOS is exact and >= 0 by construction (tests/test_hamiltonian.py:498-500);
+            # a truncated resolvent series oscillates around it and can dip below zero
+            level = max(reached, kpm.series_error(moments, gamma_min / scale))
+            warnings.warn(f"ldos: {moments} moments truncate the resolvent series at ~{level:.1e} of its leading term (broadening "
+                          f"Γ = {gamma_min:.3g}, scale = {scale:.3g}: tol = {tol:g} needs {int(np.ceil(-np.log(tol) * scale / gamma_min))}); "
+                          "the result may oscillate and turn negative", AccuracyWarning, stacklevel=3)
         # Resolvent diagonal at z = (ε + iΓ)/scale for every probe column and energy, evaluated on
         # the device from the moments (csrc/observables.cu); only [n_columns, n_energies] comes back.
         w, pref = kpm.resolvent_weights((eps + 1j * np.gradient(eps)) / scale)

@@ -34,7 +34,10 @@ def pwave(dvector: str) -> Callable:
         names[f"je_{axis}"] = 1j * eye[:, [n]]
         names[f"p_{axis}"] = eye[[n], :]
         names[f"jp_{axis}"] = 1j * eye[[n], :]
-    D = eval(dvector, {"__builtins__": {}}, names)
+    # The reference evaluates the expression inside bodge/hamiltonian.py (hamiltonian.py:446), i.e. with numpy,
+    # π, the Pauli matrices and the builtins in scope: expressions such as "np.sqrt(2) * ..." or "abs(...)" work there.
+    scope = {"np": np, "π": π, "pi": π, "σ0": σ0, "σ1": σ1, "σ2": σ2, "σ3": σ3, "jσ2": jσ2}
+    D = eval(dvector, scope, names)
 
     # gap[p] = sum_k D[k, p] * σ_k @ iσ2 / 2, so that Δ(δ) = sum_p gap[p] * δ_p.
     gap = np.einsum("kp,kab,bc->pac", D, σ, jσ2) / 2

@@ -51,11 +51,25 @@ def free_energy_from_trace(mu_trace, temperature: float, scale: float) -> float:
 def default_moments(temperature: float, scale: float, tol: float = 1e-13, cap: int = 32768) -> int:
     """Series length for a smooth integrand: the coefficients of ``g`` decay like
     ``exp(-n * pi * T / scale)`` (nearest poles of the Fermi function at ``+-i pi T``)."""
+    return free_energy_moments(temperature, scale, tol, cap)[0]
+
+
+def free_energy_moments(temperature: float, scale: float, tol: float = 1e-13, cap: int = 32768) -> tuple[int, float]:
+    """``(n, reached)``: series length for a relative truncation error ``tol`` of ``Tr g(H)`` and the error level
+    actually reached with it.  T > 0: the coefficients decay like ``exp(-n pi T / scale)``; when the length that
+    ``tol`` asks for exceeds ``cap`` the series stops there and ``reached = exp(-cap pi T / scale) > tol``.
+    T = 0: ``g`` has a kink at the Fermi level, the coefficients decay only like ``1/n^2`` and ``reached`` is about
+    ``(scale / n)^2``-limited -- 1e-7 relative at the default 8192 (measured) -- whatever ``tol`` says."""
     if temperature <= 0:
-        return 8192  # |e| kink at zero: algebraic convergence, ~1e-7 relative (documented)
-    n = int(math.ceil(-math.log(tol) * scale / (math.pi * temperature)))
-    n = max(64, min(cap, n))
-    return n + (n & 1)
+        n = 8192 if cap >= 8192 else cap + (cap & 1)
+        return n, 1e-7 * (8192 / n) ** 2
+    rate = math.pi * temperature / scale
+    n = int(math.ceil(-math.log(tol) / rate))
+    reached = tol
+    if n > cap:
+        n, reached = cap, math.exp(-cap * rate)
+    n = max(64, n)
+    return n + (n & 1), reached
 
 
 def resolvent_diagonal(mu, z: complex) -> complex:
@@ -101,9 +115,24 @@ def ldos_from_resolvent(g_imag, eps, energies) -> np.ndarray:
 
 def ldos_moments_needed(scale: float, gamma_min: float, tol: float = 1e-13, cap: int = 1 << 20) -> int:
     """The resolvent series is geometric with ratio ``|exp(-i t)| ~ 1 - Γ/scale``."""
-    n = int(math.ceil(-math.log(tol) * scale / gamma_min))
-    n = max(64, min(cap, n))
-    return n + (n & 1)
+    return ldos_moments(scale, gamma_min, tol, cap)[0]
+
+
+def ldos_moments(scale: float, gamma_min: float, tol: float = 1e-13, cap: int = 1 << 20) -> tuple[int, float]:
+    """``(n, reached)`` like ``free_energy_moments``: length of the resolvent series for a truncation error ``tol``
+    relative to its first term at broadening ``gamma_min``, and the level reached if ``cap`` cuts it short."""
+    rate = gamma_min / scale
+    n = int(math.ceil(-math.log(tol) / rate))
+    reached = tol
+    if n > cap:
+        n, reached = cap, math.exp(-cap * rate)
+    n = max(64, n)
+    return n + (n & 1), reached
+
+
+def series_error(n_moments: int, rate: float) -> float:
+    """Truncation level ``exp(-n rate)`` of a geometric series cut after ``n_moments`` terms."""
+    return math.exp(-min(n_moments * rate, 700.0))
 
 
 def ldos_from_site_moments(mu4, energies, scale: float) -> np.ndarray:
