@@ -12,6 +12,7 @@ from .helpers import *
 from .lattice import *
 
 from ._native import release_cached
+from .distributed import Replicas
 from .hamiltonian import AccuracyWarning
 
 __version__ = "0.2.0"
@@ -22,5 +23,5 @@ __all__ = [
     "pi", "sigma", "sigma0", "sigma1", "sigma2", "sigma3",
     "jsigma", "jsigma0", "jsigma1", "jsigma2", "jsigma3",
     # additions of this implementation
-    "AccuracyWarning", "release_cached",
+    "AccuracyWarning", "Replicas", "release_cached",
 ]

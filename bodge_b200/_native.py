@@ -46,6 +46,7 @@ SIGNATURES = {
     "bdg_lookup": [_vp, C.c_int64, _vp, _vp, _vp, _i64p],
     "bdg_scatter": [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_double, _f64p, _i64p],
     "bdg_clear": [_vp],
+    "bdg_stats": [_vp, _i64p],
     "bdg_export_bsr": [_vp, C.c_int, _i64p, _vp, _vp, _vp],
     "bdg_export_csr": [_vp, C.c_int, _i64p, _vp, _vp, _vp],
     "bdg_export_dense": [_vp, _vp],
@@ -57,6 +58,8 @@ SIGNATURES = {
     "bdg_cheb_available": [_vp, C.POINTER(C.c_int32)],
     "bdg_cheb_moments_read": [_vp, C.c_int32, C.c_int, _vp, C.c_int],
     "bdg_cheb_moments": [_vp, C.c_int, C.c_int32, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_int32, C.c_int, _vp, C.c_int],
+    "bdg_cheb_moments_multi": [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _vp, C.c_uint64, C.c_double, C.c_int32, C.c_int, _vp],
+    "bdg_multi_release": [],
     "bdg_cheb_vectors": [_vp, C.c_int, _vp],
     "bdg_cheb_info": [_vp, _i64p, _i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64p],
     "bdg_cheb_format": [_vp, C.POINTER(C.c_int32), _i64p, _i64p],
@@ -134,6 +137,24 @@ def check(rc: int):
 def release_cached(device: int = 0) -> None:
     """Return the library's cache of released device buffers to the CUDA driver."""
     check(load().bdg_release_cached(int(device)))
+
+
+def cheb_moments_multi(systems, n_moments: int, *, probe_rows=None, n_random: int = 0, seed: int = 0, scale: float,
+                       summed: bool = False) -> np.ndarray:
+    """``bdg_cheb_moments_multi``: one process, one ``System`` (replica of the same Hamiltonian) per GPU; the columns
+    are sharded over them and one NCCL collective combines the moments.  Returns ``[n_moments]`` (summed) or
+    ``[n_moments, n_cols]``."""
+    lib = load()
+    handles = (_vp * len(systems))(*[s._h for s in systems])
+    if probe_rows is not None:
+        rows = _as(probe_rows, np.int64)
+        kind, n_cols, rows_ptr = X0_PROBE, len(rows), _ptr(rows)
+    else:
+        kind, n_cols, rows_ptr = X0_RADEMACHER, int(n_random), None
+    out = np.empty((n_moments,) if summed else (n_moments, n_cols), dtype=np.float64)
+    check(lib.bdg_cheb_moments_multi(handles, len(systems), kind, n_cols, rows_ptr, C.c_uint64(int(seed)), float(scale),
+                                     int(n_moments), MU_SUM if summed else MU_PER_COLUMN, _ptr(out)))
+    return out
 
 
 def device_count() -> int:
@@ -247,6 +268,12 @@ class System:
 
     def clear(self):
         check(load().bdg_clear(self._h))
+
+    def stats(self) -> dict:
+        """Counters of the rebuild / patch-in-place decisions (``bdg_stats``)."""
+        out = (C.c_int64 * 5)()
+        check(load().bdg_stats(self._h, out))
+        return dict(zip(("compactions", "native_builds", "patched_scatters", "patched_blocks", "listed_hermitian_checks"), list(out)))
 
     def export_bsr(self, eliminate_zeros: bool):
         lib = load()

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbdg.so")
 PACK = os.path.join(PKG, "_bdgpack.so")  # host-side dict packer (CPython API, no CUDA): csrc/pack_dict.c
-SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu", "cheb_pair.cu", "observables.cu"]
+SOURCES = ["assemble.cu", "scan.cu", "cheb.cu", "cheb_ell.cu", "cheb_pair.cu", "observables.cu", "multi.cu"]
 
 
 def nvcc_path() -> str:
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", target,
+        "-o", target, "-ldl",
     ] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -196,6 +196,10 @@ extern "C" int bdg_destroy(bdg_t *sys) {
     free_bsr(sys, sys->packed);
     for (auto &b : sys->scratch_i32) dev_free(sys, b);
     for (auto &b : sys->stage) dev_free(sys, b);
+    dev_free(sys, sys->pack_flags);
+    dev_free(sys, sys->pack_pos);
+    dev_free(sys, sys->multi_send);
+    dev_free(sys, sys->multi_recv);
     dev_free(sys, sys->scalars);
     if (sys->host_scalars) {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
@@ -497,6 +501,37 @@ __global__ void __launch_bounds__(kThreads) hermitian_dev(int64_t n_blocks, cons
         } else {
             const double2 w = data[(int64_t)kt * 16 + b * 4 + a];
             dev = hypot(v.x - w.x, v.y + w.y);
+        }
+    }
+    atomic_max_nonneg(max_bits, dev);
+}
+
+// The same comparison for a LIST of blocks (the ones a scatter wrote; k < 0 = skip): a change of max|M - M^H| can only
+// come from a written block or its transposed partner, and the partner's comparison is this one mirrored.
+__global__ void __launch_bounds__(kThreads) hermitian_listed(int64_t n, const int32_t *__restrict__ klist,
+                                                             const int32_t *__restrict__ indptr,
+                                                             const int32_t *__restrict__ indices,
+                                                             const int32_t *__restrict__ brow,
+                                                             const double2 *__restrict__ data,
+                                                             unsigned long long *max_bits) {
+    int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int64_t e = t >> 4;
+    double dev = 0.0;
+    if (e < n) {
+        const int k = klist[e];
+        const int el = (int)(t & 15), a = el >> 2, b = el & 3;
+        const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+        int kt = 0;
+        if (el == 0 && k >= 0) kt = find_block(indptr, indices, indices[k], brow[k]);
+        kt = __shfl_sync(half_mask, kt, (threadIdx.x & 31) & 16);
+        if (k >= 0) {
+            const double2 v = data[(int64_t)k * 16 + el];
+            if (kt < 0) {
+                dev = hypot(v.x, v.y);
+            } else {
+                const double2 w = data[(int64_t)kt * 16 + b * 4 + a];
+                dev = hypot(v.x - w.x, v.y + w.y);
+            }
         }
     }
     atomic_max_nonneg(max_bits, dev);
@@ -807,8 +842,18 @@ extern "C" int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const 
     Scalars *d = sys->scalars.as<Scalars>();
     Scalars *h = static_cast<Scalars *>(sys->host_scalars);
     const BsrDev &m = sys->skel;
-    sys->packed_valid = false;
-    cheb_deactivate(sys);
+    // The recursion state is stale from here on; whether the compacted matrix and its kernel-native copies are rebuilt
+    // or patched in place is decided once the entries are in (below).
+    sys->cheb.active = false;
+    const bool was_verified = sys->herm_verified;
+    sys->herm_verified = false;
+    struct Invalidate {  // every early return leaves the copies marked stale
+        bdg_system *s;
+        bool armed = true;
+        ~Invalidate() {
+            if (armed) s->packed_valid = false, cheb_deactivate(s);
+        }
+    } invalidate{sys};
 
     BDG_TRY(reset_scalars(sys));
     // reuse `total`+`flag` (8 bytes, aligned) as first_oob
@@ -847,15 +892,52 @@ extern "C" int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const 
         bdg_set_error("%s entry %lld: block is not part of the lattice skeleton", pairing ? "pairing" : "hopping", local);
         return BDG_E_NOT_NEIGHBOUR;
     }
+    // Kernel-native copies first (the reference leaves the matrix modified when the Hermitian check raises, and so do
+    // they): patch the blocks this call wrote, or mark everything stale.
+    {
+        bool ok = sys->packed_valid && sys->ell.valid;
+        if (ok && n_hop) BDG_TRY(ell_patch(sys, n_hop, sh[3].as<int32_t>(), &ok));
+        if (ok && n_pair) BDG_TRY(ell_patch(sys, n_pair, sp[3].as<int32_t>(), &ok));
+        if (ok && n_pair) BDG_TRY(ell_patch(sys, n_pair, sp[4].as<int32_t>(), &ok));
+        invalidate.armed = !ok;
+        if (ok) sys->stats[2] += 1, sys->stats[3] += n_hop + 2 * n_pair;
+    }
     if (herm_tol >= 0.0) {
         double dev = 0.0;
-        BDG_TRY(hermitian_check(sys, &dev));
+        if (was_verified && herm_tol >= sys->herm_tol) {
+            // everything else passed this tolerance before and has not changed: look at the written blocks only
+            h->max_bits = 0ull;
+            BDG_CUDA(cudaMemcpyAsync(&d->max_bits, &h->max_bits, sizeof(unsigned long long), cudaMemcpyHostToDevice, sys->stream));
+            auto listed = [&](int64_t n, const int32_t *klist) {
+                if (n)
+                    hermitian_listed<<<grid_for(n * 16), kThreads, 0, sys->stream>>>(
+                        n, klist, m.indptr.as<int32_t>(), m.indices.as<int32_t>(), m.brow.as<int32_t>(), m.data.as<double2>(),
+                        &d->max_bits);
+            };
+            listed(n_hop, sh[3].as<int32_t>());
+            listed(n_pair, sp[3].as<int32_t>());
+            listed(n_pair, sp[4].as<int32_t>());
+            BDG_CUDA(cudaGetLastError());
+            BDG_TRY(fetch_scalars(sys));
+            memcpy(&dev, &h->max_bits, sizeof(double));
+            sys->stats[4] += 1;
+        } else {
+            BDG_TRY(hermitian_check(sys, &dev));
+        }
         if (max_dev) *max_dev = dev;
         if (dev > herm_tol) {  // NaN compares false, like np.max(...) > 1e-6 in the reference
             bdg_set_error("The constructed Hamiltonian is not Hermitian! (max deviation %.3e)", dev);
             return BDG_E_NOT_HERMITIAN;
         }
+        sys->herm_verified = true;
+        sys->herm_tol = herm_tol;
     }
+    return BDG_OK;
+}
+
+extern "C" int bdg_stats(bdg_t *sys, int64_t out[5]) {
+    BDG_REQUIRE(sys && out, "null argument");
+    for (int k = 0; k < 5; ++k) out[k] = sys->stats[k];
     return BDG_OK;
 }
 
@@ -864,6 +946,7 @@ extern "C" int bdg_clear(bdg_t *sys) {
     cheb_deactivate(sys);
     BDG_CUDA(cudaMemsetAsync(sys->skel.data.ptr, 0, (size_t)sys->skel.n_blocks * 16 * sizeof(double2), sys->stream));
     sys->packed_valid = false;
+    sys->herm_verified = false;
     return BDG_OK;
 }
 
@@ -875,6 +958,7 @@ extern "C" int bdg_import_data(bdg_t *sys, const double *data) {
                              cudaMemcpyHostToDevice, sys->stream));
     BDG_CUDA(cudaStreamSynchronize(sys->stream));
     sys->packed_valid = false;
+    sys->herm_verified = false;
     return BDG_OK;
 }
 
@@ -887,10 +971,10 @@ int build_packed(bdg_system *sys) {
     Scalars *d = sys->scalars.as<Scalars>();
     const int n = (int)m.n_sites;
     const int64_t nb = m.n_blocks;
-    BDG_TRY(ensure_scratch(sys, 0, (size_t)(nb + 1) * sizeof(int32_t)));  // flags
-    BDG_TRY(ensure_scratch(sys, 1, (size_t)(nb + 1) * sizeof(int32_t)));  // positions
-    int32_t *flags = sys->scratch_i32[0].as<int32_t>();
-    int32_t *pos = sys->scratch_i32[1].as<int32_t>();
+    BDG_TRY(dev_alloc(sys, sys->pack_flags, (size_t)(nb + 1) * sizeof(int32_t)));  // kept: a later scatter patches `packed` through them
+    BDG_TRY(dev_alloc(sys, sys->pack_pos, (size_t)(nb + 1) * sizeof(int32_t)));
+    int32_t *flags = sys->pack_flags.as<int32_t>();
+    int32_t *pos = sys->pack_pos.as<int32_t>();
     BDG_TRY(dev_alloc(sys, p.indptr, (size_t)(n + 1) * sizeof(int32_t)));
     int32_t *pptr = p.indptr.as<int32_t>();
     flag_nonzero<<<grid_for(nb * 16), kThreads, 0, sys->stream>>>(nb, m.data.as<double2>(), flags);
@@ -912,6 +996,7 @@ int build_packed(bdg_system *sys) {
                                                                     p.data.as<double2>());
     BDG_CUDA(cudaGetLastError());
     sys->packed_valid = true;
+    sys->stats[0] += 1;
     return BDG_OK;
 }
 

@@ -141,6 +141,11 @@ struct EllDev {
     int pair_M = 0;
     DevBuf dcode;  // int32 [n_sites][5]: dictionary code per stencil direction (self, x-1, y-1, y+1, x+1), -1 = none
     DevBuf tmp_keys, tmp_rep, tmp_where, tmp_dense;  // hash-table scratch of the dictionary build (kept for rebuilds)
+    // ... and what stays alive for incremental updates (ell_patch): the hash table itself (tmp_keys, `hash_cap` slots),
+    // posid[hash position] = dictionary code (-1: unused), the table's capacity in entries, device counters
+    // {n_unique, pattern changed, table full, hash collision, off-site block not real-diagonal}.
+    DevBuf posid, counters;
+    int64_t hash_cap = 0, table_cap = 0;
 };
 
 struct bdg_system {
@@ -155,6 +160,13 @@ struct bdg_system {
     BsrDev skel;           // full skeleton, values as scattered so far
     BsrDev packed;         // after eliminate_zeros (built lazily)
     bool packed_valid = false;
+    DevBuf pack_flags;     // int32 [skel.n_blocks]: block kept in `packed` (non-zero)      } kept after the compaction so that a
+    DevBuf pack_pos;       // int32 [skel.n_blocks]: its position there                      } later scatter can patch the copies
+    // Hermiticity bookkeeping: the stored matrix passed max|M - M^H| <= herm_tol and every change since went through a
+    // checked scatter -- then the next scatter only needs to look at the blocks it writes (and their transposes).
+    bool herm_verified = false;
+    double herm_tol = 0.0;
+    int64_t stats[5] = {0, 0, 0, 0, 0};  // bdg_stats
     int packed_max_row = 0;  // longest block row of `packed` (picks the kernel's unroll)
 
     DevBuf scratch_i32[4];  // reusable scratch (counts, scans, flags, positions)
@@ -164,6 +176,7 @@ struct bdg_system {
 
     ChebState cheb;
     EllDev ell;
+    DevBuf multi_send, multi_recv;  // moments of this GPU / of all GPUs around the NCCL collective (multi.cu)
 };
 
 // scan.cu
@@ -183,6 +196,10 @@ int t2_finish_dots(bdg_system *sys);    // T2 mode: dot rows -> single-step form
 int ell_build(bdg_system *sys);                    // (re)build sys->ell from sys->packed when stale
 int ell_configure(bdg_system *sys);                // pick panels_per_group / grid for the current ChebState
 int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
+// After a scatter: bring `packed` and the kernel-native copies (fixed-width rows, dictionary, direction codes) up to date
+// for the `n` skeleton blocks listed in `klist` (device; < 0 = skip) instead of rebuilding them.  *ok = false: the zero
+// pattern changed, the table is full, ...: the caller invalidates the copies and the next recursion rebuilds them.
+int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok);
 void ell_release(bdg_system *sys);
 
 // cheb_pair.cu

@@ -42,6 +42,18 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+// Stencil direction of block column `col` seen from `row` on the Lx x M torus: 0 = the row itself, 1 = x-1,
+// 2 = y-1, 3 = y+1, 4 = x+1 (wrap-around included), -1 = none of these.  Lx, M >= 3 keep the five apart.
+__device__ __forceinline__ int torus_direction(int row, int col, int Lx, int M) {
+    const int xr = row / M, yr = row - xr * M, xc = col / M, yc = col - xc * M;
+    int dx = xc - xr, dy = yc - yr;
+    dx += dx < 0 ? Lx : 0;
+    dy += dy < 0 ? M : 0;
+    if (dx == 0) return dy == 0 ? 0 : (dy == M - 1 ? 2 : (dy == 1 ? 3 : -1));
+    if (dy != 0) return -1;
+    return dx == Lx - 1 ? 1 : (dx == 1 ? 4 : -1);
+}
+
 // ---- per-step reduction of the two dot products ---------------------------------------------
 // Every lane arrives with its partial sums for column `col` (valid iff col_ok and it is the
 // designated leader lane for that column inside the warp).  CTA partials go to global memory;

@@ -334,27 +334,31 @@ dict_insert(int64_t n_slots, const double *__restrict__ cdata, unsigned long lon
     where[w] = (int32_t)pos;
 }
 
+// flag[slot] = 1 iff the slot is the representative of its key (the smallest slot id holding that block).  The
+// exclusive scan of the flags numbers the distinct blocks in SLOT order, so the table follows the matrix: the
+// on-site blocks of consecutive sites sit next to each other (a kernel that fetches a site-dependent on-site
+// block per row then streams the table instead of gathering 256-byte pieces from all over it).
 __global__ void __launch_bounds__(256)
-dict_flag_used(int64_t cap, const unsigned long long *__restrict__ keys, int32_t *__restrict__ used) {
+dict_flag_reps(int64_t n_slots, const int *__restrict__ rep, const int32_t *__restrict__ where, int32_t *__restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < cap) used[t] = keys[t] != kEmptyKey;
+    if (t < n_slots) flag[t] = rep[where[t]] == (int)t;
 }
 
-// One warp per slot: code = dense id of its table position; the representative writes the table
-// entry; everyone else is compared with the representative's bytes.
+// One warp per slot: code = rank of its representative among the representatives (dense[]: scanned flags); the
+// representative writes the table entry; everyone else is compared with the representative's bytes.
 __global__ void __launch_bounds__(256)
 dict_emit(int64_t n_slots, const double *__restrict__ cdata, const int *__restrict__ rep,
           const int32_t *__restrict__ dense, const int32_t *__restrict__ where, int32_t *__restrict__ ccode,
-          double *__restrict__ table, int table_cap, int *__restrict__ mismatch) {
+          double *__restrict__ table, int table_cap, int32_t *__restrict__ posid, int *__restrict__ mismatch) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_slots) return;
-    const int pos = where[w];
-    const int code = dense[pos];
-    const int r = rep[pos];
+    const int r = rep[where[w]];
+    const int code = dense[r];
     const long long mine = __double_as_longlong(cdata[w * 32 + lane]);
     if (r == (int)w) {
         if (code < table_cap) table[(size_t)code * 32 + lane] = __longlong_as_double(mine);
+        if (lane == 0) posid[where[w]] = code;  // hash position -> code: later updates look new blocks up here (ell_patch)
     } else if (mine != __double_as_longlong(cdata[(int64_t)r * 32 + lane])) {
         *mismatch = 1;
     }
@@ -382,6 +386,128 @@ dict_offsite_diag(int64_t n_slots, int width, const int32_t *__restrict__ ccode,
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_slots || t % width == 0) return;
     if (!isdiag[ccode[t]]) *bad = 1;
+}
+
+// ---- incremental update after a scatter (re-enter `with`, change a few terms, ask again) -----------
+// One warp per touched skeleton block: copy it into its place in `packed`, into its fixed-width slot (fragment
+// order), look it up in -- or add it to -- the dictionary and rewrite the slot's code (and direction code).
+// status: [0] distinct blocks so far, [1] zero pattern changed, [2] table full, [3] hash collision, [4] an
+// off-site block that is not real-diagonal (the DIAG kernels no longer apply).
+struct PatchArgs {
+    const int32_t *s_indices, *s_brow;
+    const double *s_data;
+    const int32_t *flags, *pos;
+    double *p_data;
+    int width;
+    const int32_t *cidx;
+    double *cdata;
+    int32_t *ccode;
+    int dict;
+    unsigned long long *keys;
+    int32_t *posid;
+    unsigned cap_mask;
+    double *table, *dtab;
+    int table_cap, diag_required;
+    int32_t *dcode;
+    int Lx, M;
+    int *status;
+};
+
+__global__ void __launch_bounds__(256)
+patch_blocks(int64_t n, const int32_t *__restrict__ klist, const PatchArgs a) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int k = klist[w];
+    if (k < 0) return;
+    const double vs = a.s_data[(size_t)k * 32 + lane];  // skeleton order: (row a, column b, re/im) = double (a*4+b)*2+part
+    const bool nz = __ballot_sync(kFull, vs != 0.0) != 0u;
+    if (nz != (a.flags[k] != 0)) {
+        if (lane == 0) a.status[1] = 1;
+        return;
+    }
+    if (!nz) return;
+    a.p_data[(size_t)a.pos[k] * 32 + lane] = vs;
+    if (a.width == 0) return;
+    const int row = a.s_brow[k], col = a.s_indices[k];
+    int u = 0;
+    if (col != row) {
+        const bool hit = lane >= 1 && lane < a.width && a.cidx[(size_t)row * a.width + lane] == col;
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (m == 0u) {  // cannot happen for a block that was already stored
+            if (lane == 0) a.status[1] = 1;
+            return;
+        }
+        u = __ffs(m) - 1;
+    }
+    const int64_t slot = (int64_t)row * a.width + u;
+    const int fa = lane >> 3, part = (lane >> 2) & 1, fb = lane & 3;  // fragment order (ell_fill)
+    const double f = a.s_data[(size_t)k * 32 + (fa * 4 + fb) * 2 + part];
+    a.cdata[slot * 32 + lane] = f;
+    if (!a.dict) return;
+    uint64_t h = mix64((uint64_t)__double_as_longlong(f) + 0x9E3779B97F4A7C15ull * (uint64_t)(lane + 1));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(kFull, h, d);
+    h = mix64(h);
+    if (h == kEmptyKey) h = 0x1234567ull;
+    int id = -1, won = 0;
+    unsigned pos = 0;
+    if (lane == 0) {
+        pos = (unsigned)h & a.cap_mask;
+        for (;;) {
+            unsigned long long seen = *((volatile unsigned long long *)(a.keys + pos));
+            if (seen == kEmptyKey) {
+                seen = atomicCAS(a.keys + pos, kEmptyKey, (unsigned long long)h);
+                if (seen == kEmptyKey) {
+                    won = 1;
+                    id = atomicAdd(a.status, 1);
+                    if (id >= a.table_cap) {
+                        a.status[2] = 1;
+                        id = -2;
+                    }
+                    break;
+                }
+            }
+            if (seen == h) break;
+            pos = (pos + 1) & a.cap_mask;
+        }
+        if (!won) {  // someone holds the key: its code is published once the table entry is in place
+            while ((id = *((volatile int32_t *)(a.posid + pos))) == -1) {}
+        }
+    }
+    id = __shfl_sync(kFull, id, 0);
+    won = __shfl_sync(kFull, won, 0);
+    pos = __shfl_sync(kFull, pos, 0);
+    const bool on_diag = part == 0 && fa == fb;
+    const bool isdiag = __ballot_sync(kFull, !on_diag && f != 0.0) == 0u;
+    if (won) {
+        if (id >= 0) {
+            a.table[(size_t)id * 32 + lane] = f;
+            if (on_diag) a.dtab[(size_t)id * 4 + fa] = f;
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) *((volatile int32_t *)(a.posid + pos)) = id;
+    }
+    if (id < 0) {
+        if (lane == 0) a.status[2] = 1;
+        return;
+    }
+    if (!won) {
+        const double have = *((volatile const double *)(a.table + (size_t)id * 32 + lane));
+        if (__ballot_sync(kFull, __double_as_longlong(have) != __double_as_longlong(f)) != 0u) {
+            if (lane == 0) a.status[3] = 1;
+            return;
+        }
+    }
+    if (lane == 0) {
+        if (u > 0 && a.diag_required && !isdiag) a.status[4] = 1;
+        a.ccode[slot] = id;
+        if (a.dcode) {
+            const int dir = u == 0 ? 0 : torus_direction(row, col, a.Lx, a.M);
+            if (dir >= 0) a.dcode[(size_t)row * 5 + dir] = id;
+        }
+    }
 }
 
 using EllKernel = void (*)(const int32_t *, const int32_t *, const double *, const double *, const double2 *, double2 *,
@@ -485,7 +611,7 @@ int dict_build(bdg_system *sys) {
         const int limit = (int)std::min<int64_t>(cap / 2, max_unique);
         BDG_TRY(dev_alloc(sys, e.tmp_keys, (size_t)cap * sizeof(unsigned long long)));
         BDG_TRY(dev_alloc(sys, e.tmp_rep, (size_t)cap * sizeof(int)));
-        BDG_TRY(dev_alloc(sys, e.tmp_dense, (size_t)(cap + 1) * sizeof(int32_t)));
+        BDG_TRY(dev_alloc(sys, e.tmp_dense, (size_t)(n_slots + 1) * sizeof(int32_t)));
         BDG_CUDA(cudaMemsetAsync(e.tmp_keys.ptr, 0xff, (size_t)cap * sizeof(unsigned long long), sys->stream));
         BDG_CUDA(cudaMemsetAsync(e.tmp_rep.ptr, 0x7f, (size_t)cap * sizeof(int), sys->stream));
         BDG_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), sys->stream));
@@ -500,16 +626,25 @@ int dict_build(bdg_system *sys) {
         if (limit >= max_unique) return BDG_OK;  // too many distinct blocks: keep the plain format
         cap <<= 4;
     }
-    dict_flag_used<<<(unsigned)ceil_div(cap, 256), 256, 0, sys->stream>>>(cap, e.tmp_keys.as<unsigned long long>(),
-                                                                          e.tmp_dense.as<int32_t>());
+    dict_flag_reps<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(n_slots, e.tmp_rep.as<int>(), e.tmp_where.as<int32_t>(),
+                                                                              e.tmp_dense.as<int32_t>());
     BDG_CUDA(cudaGetLastError());
-    BDG_TRY(exclusive_scan_i32(sys, e.tmp_dense.as<int32_t>(), e.tmp_dense.as<int32_t>(), cap, scal + 2));
+    BDG_TRY(exclusive_scan_i32(sys, e.tmp_dense.as<int32_t>(), e.tmp_dense.as<int32_t>(), n_slots, scal + 2));
     const int n_unique = host[0];
+    // Head room for blocks that later scatters add (ell_patch): half as many again, at least 64 Ki, and never more than
+    // three quarters of the hash table.
+    e.hash_cap = cap;
+    e.table_cap = std::min<int64_t>(std::max<int64_t>(n_unique + n_unique / 2, n_unique + 65536), cap * 3 / 4);
+    e.table_cap = std::max<int64_t>(e.table_cap, n_unique);
     BDG_TRY(dev_alloc(sys, e.code, (size_t)n_slots * sizeof(int32_t)));
-    BDG_TRY(dev_alloc(sys, e.table, (size_t)n_unique * 32 * sizeof(double)));
+    BDG_TRY(dev_alloc(sys, e.table, (size_t)e.table_cap * 32 * sizeof(double)));
+    BDG_TRY(dev_alloc(sys, e.posid, (size_t)cap * sizeof(int32_t)));
+    BDG_TRY(dev_alloc(sys, e.counters, 8 * sizeof(int)));
+    BDG_CUDA(cudaMemsetAsync(e.posid.ptr, 0xff, (size_t)cap * sizeof(int32_t), sys->stream));
     dict_emit<<<warps_grid, 256, 0, sys->stream>>>(n_slots, e.data.as<double>(), e.tmp_rep.as<int>(),
                                                    e.tmp_dense.as<int32_t>(), e.tmp_where.as<int32_t>(),
-                                                   e.code.as<int32_t>(), e.table.as<double>(), n_unique, scal + 3);
+                                                   e.code.as<int32_t>(), e.table.as<double>(), n_unique, e.posid.as<int32_t>(),
+                                                   scal + 3);
     BDG_CUDA(cudaGetLastError());
     BDG_CUDA(cudaMemcpyAsync(host + 2, scal + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
     BDG_CUDA(cudaStreamSynchronize(sys->stream));
@@ -517,7 +652,7 @@ int dict_build(bdg_system *sys) {
     // Real-diagonal off-site blocks (DIAG kernels)?
     e.diag_usable = false;
     if (e.dict_usable) {
-        BDG_TRY(dev_alloc(sys, e.dtab, (size_t)n_unique * 4 * sizeof(double)));
+        BDG_TRY(dev_alloc(sys, e.dtab, (size_t)e.table_cap * 4 * sizeof(double)));
         BDG_TRY(dev_alloc(sys, e.tmp_rep, (size_t)std::max<int64_t>(cap, n_unique) * sizeof(int)));  // reuse as isdiag[]
         BDG_CUDA(cudaMemsetAsync(scal, 0, sizeof(int), sys->stream));
         dict_diag_table<<<(unsigned)ceil_div((int64_t)n_unique * 32, 256), 256, 0, sys->stream>>>(
@@ -545,6 +680,8 @@ void ell_release(bdg_system *sys) {
     dev_free(sys, sys->ell.tmp_rep);
     dev_free(sys, sys->ell.tmp_where);
     dev_free(sys, sys->ell.tmp_dense);
+    dev_free(sys, sys->ell.posid);
+    dev_free(sys, sys->ell.counters);
     sys->ell = EllDev();
 }
 
@@ -588,6 +725,54 @@ int ell_build(bdg_system *sys) {
         }
     }
     e.valid = true;
+    sys->stats[1] += 1;
+    return BDG_OK;
+}
+
+int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok) {
+    EllDev &e = sys->ell;
+    *ok = false;
+    if (!sys->packed_valid || !e.valid || !sys->pack_flags.ptr || !sys->pack_pos.ptr) return BDG_OK;
+    if (env_int("BDG_NO_PATCH", 0)) return BDG_OK;  // A/B: always rebuild
+    if (n == 0) {
+        *ok = true;
+        return BDG_OK;
+    }
+    const bool dict = e.usable && e.dict_usable;
+    if (e.usable && !dict && e.n_unique > 0) return BDG_OK;  // a dictionary was attempted and given up: rebuild decides again
+    BDG_TRY(dev_alloc(sys, e.counters, 8 * sizeof(int)));
+    int host[5] = {(int)e.n_unique, 0, 0, 0, 0};
+    BDG_CUDA(cudaMemcpyAsync(e.counters.ptr, host, sizeof(host), cudaMemcpyHostToDevice, sys->stream));
+    PatchArgs a{};
+    a.s_indices = sys->skel.indices.as<int32_t>();
+    a.s_brow = sys->skel.brow.as<int32_t>();
+    a.s_data = sys->skel.data.as<double>();
+    a.flags = sys->pack_flags.as<int32_t>();
+    a.pos = sys->pack_pos.as<int32_t>();
+    a.p_data = sys->packed.data.as<double>();
+    a.width = e.usable ? e.width : 0;
+    a.cidx = e.idx.as<int32_t>();
+    a.cdata = e.data.as<double>();
+    a.ccode = e.code.as<int32_t>();
+    a.dict = dict ? 1 : 0;
+    a.keys = e.tmp_keys.as<unsigned long long>();
+    a.posid = e.posid.as<int32_t>();
+    a.cap_mask = (unsigned)(e.hash_cap - 1);
+    a.table = e.table.as<double>();
+    a.dtab = e.dtab.as<double>();
+    a.table_cap = (int)e.table_cap;
+    a.diag_required = e.diag_usable ? 1 : 0;
+    a.dcode = e.pair_usable ? e.dcode.as<int32_t>() : nullptr;
+    a.Lx = sys->cubic[0];
+    a.M = e.pair_M;
+    a.status = e.counters.as<int>();
+    patch_blocks<<<(unsigned)ceil_div(n * 32, 256), 256, 0, sys->stream>>>(n, klist, a);
+    BDG_CUDA(cudaGetLastError());
+    BDG_CUDA(cudaMemcpyAsync(host, e.counters.ptr, sizeof(host), cudaMemcpyDeviceToHost, sys->stream));
+    BDG_CUDA(cudaStreamSynchronize(sys->stream));
+    if (host[1] || host[2] || host[3] || host[4]) return BDG_OK;  // pattern / capacity / collision / DIAG precondition: rebuild
+    e.n_unique = host[0];
+    *ok = true;
     return BDG_OK;
 }
 

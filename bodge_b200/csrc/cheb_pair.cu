@@ -176,9 +176,11 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
     yi = r.yi;
 }
 
+#ifdef BDG_PAIR_SPLIT
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+#endif
 
 // NW warps per CTA, two ADJACENT sites per warp and plane: W = 2 NW sites per plane in sub-step [A]
 // (P <= W - 2 of them owned).  Dynamic shared memory: kRingN planes of W + 2 records (T_n), kRing
@@ -242,7 +244,9 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
     __syncthreads();
     uint32_t cnt = 0;  // T_n planes consumed by the items before this one
+#ifdef BDG_PAIR_SPLIT
     uint32_t xphase = 0;  // parity of the hand-over barrier's current phase (one phase per iteration)
+#endif
     const size_t gstep = (size_t)wk.M * 32;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 
@@ -312,8 +316,13 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         int cplane = x0 - 1;  // plane of [A] in iteration 0
         cplane += cplane < 0 ? wk.Lx : 0;
         cplane *= plane_codes;
-        int jvA = -1, jvB = -1;
+        // codes of the planes of [A] in this iteration, [B] (one plane behind), and of the next two planes of [A]: loaded
+        // two planes ahead, so that the on-site fragment fetch of the next plane (SELF) never waits for its code
+        int jvA = -1, jvB = -1, jnext = -1;
         if (code_lane) jvA = __ldg(dcode + cplane + coff);
+        cplane += plane_codes;
+        cplane -= cplane >= all_codes ? all_codes : 0;
+        if (code_lane) jnext = __ldg(dcode + cplane + coff);
         double fsA[S], fsB[S], fsN[S];  // SELF: on-site fragments of the planes of [A], [B] and of the next [A]
 #pragma unroll
         for (int s = 0; s < S; ++s) fsA[s] = fsB[s] = fsN[s] = 0.0;
@@ -380,12 +389,12 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 }
             }
             wait(i + 2);
-            int jnext = -1;
+            int jn2 = -1;
             cplane += plane_codes;
             cplane -= cplane >= all_codes ? all_codes : 0;
-            if (code_lane && i <= len) jnext = __ldg(dcode + cplane + coff);
+            if (code_lane && i < len) jn2 = __ldg(dcode + cplane + coff);
             if (SELF) self_fragments<S>(jnext, fsN, table, lane);
-            double2 tn[S];  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
+            double2 tn[S] = {};  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
             // [B]: update, store and dot products of row s from its product (yr, yi) and its own T_{n+1} record
             auto finish_b = [&](int s, double yr, double yi, const double2 &own1) {
                 const double2 t = tn[s];
@@ -508,6 +517,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #endif
             jvB = jvA;
             jvA = jnext;
+            jnext = jn2;
 #pragma unroll
             for (int s = 0; s < S; ++s) fsB[s] = fsA[s], fsA[s] = fsN[s];
         }
@@ -562,18 +572,6 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         dots_step[(size_t)(threadIdx.x >> 3) * n_panels * 8 + panel * 8 + (threadIdx.x & 7)] = t;
     }
     if (threadIdx.x == 0) tickets[panel] = 0u;
-}
-
-// Stencil direction of block column `col` seen from `row` on the Lx x M torus: 0 = the row itself, 1 = x-1,
-// 2 = y-1, 3 = y+1, 4 = x+1 (wrap-around included), -1 = none of these.  Lx, M >= 3 keep the five apart.
-__device__ __forceinline__ int torus_direction(int row, int col, int Lx, int M) {
-    const int xr = row / M, yr = row - xr * M, xc = col / M, yc = col - xc * M;
-    int dx = xc - xr, dy = yc - yr;
-    dx += dx < 0 ? Lx : 0;
-    dy += dy < 0 ? M : 0;
-    if (dx == 0) return dy == 0 ? 0 : (dy == M - 1 ? 2 : (dy == 1 ? 3 : -1));
-    if (dy != 0) return -1;
-    return dx == Lx - 1 ? 1 : (dx == 1 ? 4 : -1);
 }
 
 // *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its four nearest

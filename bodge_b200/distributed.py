@@ -59,3 +59,51 @@ def combine(local: np.ndarray, summed: bool, n_total: int, rank: int, world: int
         lo, hi = shard_range(n_total, r, world)
         out[:, lo:hi] = part.cpu().numpy()[:, : hi - lo]
     return out
+
+
+class Replicas:
+    """ONE process driving several GPUs through the C ABI's own multi-GPU entry point (``bdg_cheb_moments_multi``):
+    a replica of the Hamiltonian per device, the start columns sharded over them, one NCCL collective at the end --
+    no torch, no process group.  (With ``torchrun`` -- one process per GPU -- ``Hamiltonian`` shards over the
+    initialised ``torch.distributed`` group by itself; this is the same partition for callers that own all GPUs.)
+
+        systems = Replicas(CubicLattice((1000, 1000, 1)), devices=[0, 1, 2, 3])
+        systems.fill(*packed)                       # or:  with systems as (H, Δ): ...
+        mu = systems.chebyshev_moments(2048, vectors=64, summed=True)
+    """
+
+    def __init__(self, lattice, devices):
+        from .hamiltonian import Hamiltonian
+
+        if len(set(devices)) != len(devices) or not devices:
+            raise ValueError("one replica per device: give a list of distinct device indices")
+        self.devices = list(devices)
+        self.replicas = [Hamiltonian(lattice, device=d) for d in self.devices]
+        self.lattice = lattice
+
+    # the reference's context manager, applied to every replica
+    def __enter__(self):
+        self._hopp, self._pair = {}, {}
+        return self._hopp, self._pair
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        from .hamiltonian import _pack_entries
+
+        packed = _pack_entries(self.lattice, self._hopp) + _pack_entries(self.lattice, self._pair)
+        self.fill(*packed)
+        del self._hopp, self._pair
+
+    def fill(self, *packed, **kw):
+        return max(r.fill(*packed, **kw) for r in self.replicas)
+
+    def spectral_bound(self):
+        return self.replicas[0].spectral_bound()
+
+    def chebyshev_moments(self, moments: int, *, rows=None, vectors=None, seed: int = 1234, scale=None, summed: bool = False):
+        from . import _native
+
+        if (rows is None) == (vectors is None):
+            raise ValueError("give either rows= (probe columns) or vectors= (random columns)")
+        scale = self.spectral_bound() if scale is None else float(scale)
+        return _native.cheb_moments_multi([r._sys for r in self.replicas], int(moments), probe_rows=rows,
+                                          n_random=0 if vectors is None else int(vectors), seed=seed, scale=scale, summed=summed)

@@ -88,6 +88,14 @@ int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const int32_t *h_
                 const double *p_val, double herm_tol, double *max_dev, int64_t *bad_entry);
 /* Set every stored value back to zero (fresh skeleton). */
 int bdg_clear(bdg_t *sys);
+/* Incremental updates (the reference's parameter-sweep idiom: re-enter `with` for a few keys, ask for an observable
+ * again -- tests/test_physics.py:155-160, 221-224; its scatter touches only the keys set, bodge/hamiltonian.py:102-118).
+ * bdg_scatter patches the compacted matrix and the step kernels' own copies of it (fixed-width rows, block dictionary,
+ * direction codes) for the blocks it writes, and checks Hermiticity on those blocks only, whenever the zero pattern is
+ * unchanged and the stored matrix had passed the check before; otherwise the copies are rebuilt by the next recursion.
+ * out[0] = compactions (eliminate_zeros) so far, out[1] = builds of the kernel-native copies, out[2] = scatters that
+ * were patched in place, out[3] = blocks patched, out[4] = Hermitian checks restricted to the written blocks. */
+int bdg_stats(bdg_t *sys, int64_t out[5]);
 
 /* ---- export: replaces Hamiltonian.matrix("bsr") / ._matrix (bodge/hamiltonian.py:128-143) */
 /* Two-phase: call with indptr = indices = data = NULL to get *n_blocks, then with buffers
@@ -171,6 +179,17 @@ int bdg_cheb_moments_read(bdg_t *sys, int32_t n_moments, int reduce, double *mu,
 int bdg_cheb_moments(bdg_t *sys, int kind, int32_t n_cols, const int64_t *probe_rows,
                      uint64_t seed, int64_t col_offset, double scale, int32_t n_moments,
                      int reduce, double *mu, int mu_on_device);
+/* Several GPUs, one process (the reference is single-device, README.md:36-39): sys[g] holds a replica of
+ * the SAME Hamiltonian on GPU g (create + scatter it on each; one handle per device).  The n_cols start columns -- probe
+ * rows, or Rademacher columns 0 .. n_cols-1 of `seed` -- are split contiguously over the GPUs (the first n_cols %% n_gpu
+ * shards take one more), every GPU runs its recursion without communication, and ONE NCCL collective on the handles'
+ * streams combines the result: all-reduce of the summed moments (BDG_MU_SUM: mu[n_moments]) or all-gather of the
+ * per-column ones (BDG_MU_PER_COLUMN: mu[n_moments][n_cols], columns in their original order).  mu is a host buffer.
+ * NCCL is loaded at run time (libnccl.so.2, or $BDG_NCCL_LIB); the communicators of a device list are created on
+ * first use and kept (bdg_multi_release destroys them).  n_gpu = 1 is bdg_cheb_moments. */
+int bdg_cheb_moments_multi(bdg_t **sys, int n_gpu, int kind, int64_t n_cols, const int64_t *probe_rows,
+                           uint64_t seed, double scale, int32_t n_moments, int reduce, double *mu);
+int bdg_multi_release(void);
 /* Copy the current T_n ([4N, n_cols] row-major complex128) to the host (testing / debugging). */
 int bdg_cheb_vectors(bdg_t *sys, int which /*0 = T_n, 1 = T_{n-1}*/, double *out);
 /* Algorithmic bytes of one step at the current configuration (SURVEY 8d formula) and the

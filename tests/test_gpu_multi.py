@@ -71,3 +71,49 @@ def test_column_sharding_two_gpus(gpu_api, tmp_path):
         assert rel_err(got["trace"], want.sum(axis=1)) <= 1e-10
         assert np.allclose(got["rho"], rho1, rtol=1e-10, atol=1e-12)
         assert abs(float(got["F"]) - F1) <= 1e-11 * abs(F1)
+
+
+def test_c_abi_multi_gpu_entry_point(gpu_api):
+    """One process, two GPUs, through the raw C ABI (``bdg_cheb_moments_multi``, NCCL inside): the sharded
+    result equals the single-GPU one per column (bit for bit: a column's arithmetic does not depend on which GPU it
+    runs on when the panels line up) and the oracle's to 1e-10, for summed moments, per-column moments and probe columns."""
+    import ctypes as C
+
+    import bodge_b200 as b
+    from bodge_b200 import _native, workloads
+
+    if _native.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    shape = (18, 12, 1)
+    packed = workloads.junction(shape)
+    replicas = b.Replicas(b.CubicLattice(shape), devices=[0, 1])
+    assert replicas.fill(*packed) == 0.0
+    single = replicas.replicas[0]
+    scale = single.spectral_bound()
+    H = single.matrix("bsr")
+    want = orc.cheb_moments(H, orc.rademacher(5, H.shape[0], np.arange(16)), 30, scale)
+    # raw ABI call, no Python helper in between
+    lib = _native.load()
+    handles = (C.c_void_p * 2)(*[r._sys._h for r in replicas.replicas])
+    mu = np.empty((30, 16))
+    rc = lib.bdg_cheb_moments_multi(handles, 2, _native.X0_RADEMACHER, 16, None, C.c_uint64(5), scale, 30, _native.MU_PER_COLUMN,
+                                    mu.ctypes.data_as(C.c_void_p))
+    assert rc == 0, _native.last_error()
+    assert rel_err(mu, want) <= 1e-10
+    assert np.array_equal(mu, single.chebyshev_moments(30, vectors=16, seed=5, scale=scale, group=None))  # 8 + 8 columns: whole panels
+    # helper: uneven shards (11 = 6 + 5), summed and per column, probe columns
+    got = replicas.chebyshev_moments(30, vectors=11, seed=5, scale=scale)
+    assert rel_err(got, want[:, :11]) <= 1e-10
+    total = replicas.chebyshev_moments(30, vectors=11, seed=5, scale=scale, summed=True)
+    assert rel_err(total, want[:, :11].sum(axis=1)) <= 1e-10
+    rows = single._probe_rows([(3, 4, 0), (9, 9, 0), (17, 0, 0)])
+    probe = replicas.chebyshev_moments(30, rows=rows, scale=scale)
+    assert rel_err(probe, orc.cheb_moments(H, orc.probes(H.shape[0], rows), 30, scale)) <= 1e-10
+    # the dict API on all replicas at once, then an incremental update that every replica follows
+    with replicas as (Hd, Dd):
+        Hd[(2, 2, 0), (2, 2, 0)] = 2.5 * gpu_api.σ0
+    H2 = single.matrix("bsr")
+    scale2 = replicas.spectral_bound()
+    again = replicas.chebyshev_moments(30, vectors=16, seed=5, scale=scale2, summed=True)
+    assert rel_err(again, orc.cheb_moments(H2, orc.rademacher(5, H2.shape[0], np.arange(16)), 30, scale2).sum(axis=1)) <= 1e-10
+    assert lib.bdg_multi_release() == 0
