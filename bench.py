@@ -20,7 +20,8 @@ back to the host inside the timed region); ``roofline`` = the dominant kernel ag
 ``frac`` on the bytes it MOVES (ncu DRAM bytes of the committed capture when there is one, else the format's own
 accounting), the SURVEY-8d algorithmic-bytes figure beside it as ``speedup_vs_one_pass_roofline``;
 ``block_repetition`` = the same lattice with 10^6 distinct on-site blocks and with every block distinct;
-``other_configs`` = BASELINE configs C2, C3, C4; ``strong_scaling`` = 64 columns in total; ``parity_check`` =
+``other_configs`` = BASELINE configs C2, C3, C4; ``strong_scaling`` = 64 columns in total; ``incremental_update`` = cost of
+the reference's parameter-sweep idiom (re-enter ``with``, start the next recursion), patched vs rebuilt; ``parity_check`` =
 the first moments against the CPU oracle (N = 1) / against a single-GPU recomputation of all shards (N > 1);
 ``cpu_baseline`` = scipy's bsr_matvecs recursion on the host cores (oracle port).
 
@@ -365,6 +366,43 @@ class Bench:
                 "speedup_vs_one_pass_roofline": alg / self.peak}
 
 
+def incremental_update_cost(b, system, scale, n_sites):
+    """`fill()` of 16 / of N/2 on-site terms followed by `bdg_cheb_begin` (the first launch of the next
+    recursion included), with the copies patched in place -- and, for comparison, rebuilt (BDG_NO_PATCH=1)."""
+    s = system._sys
+    out = {}
+
+    def begin():
+        s.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto_moments")
+        s.sync()
+
+    begin()
+    for label, sites in (("16_terms", np.arange(0, n_sites, max(n_sites // 16, 1), dtype=np.int32)[:16]),
+                         ("half_the_sites", np.arange(n_sites // 2, dtype=np.int32))):
+        for mode in ("patched", "rebuilt"):
+            if mode == "rebuilt":
+                os.environ["BDG_NO_PATCH"] = "1"
+            rows = []
+            for rep in range(4):
+                vals = np.broadcast_to((3.0 + 0.01 * rep) * b.σ0 - 0.3 * b.σ3, (len(sites), 2, 2)).astype(np.complex128).copy()
+                s.sync()
+                t0 = time.perf_counter()
+                system.fill(sites, sites, vals)
+                s.sync()
+                t1 = time.perf_counter()
+                begin()
+                rows.append((t1 - t0, time.perf_counter() - t1))
+            os.environ.pop("BDG_NO_PATCH", None)
+            fill_ms, begin_ms = (1e3 * statistics.median(r[k] for r in rows[1:]) for k in (0, 1))
+            out[f"{label}_{mode}"] = {"entries": int(len(sites)), "fill_ms": fill_ms, "next_recursion_begin_ms": begin_ms,
+                                      "h2d_bytes": int(len(sites)) * 72}
+    out["stats"] = s.stats()
+    out["what"] = ("Hamiltonian.fill(on-site terms from pageable host memory: H2D + lookup + scatter + symmetry fill + Hermitian check "
+                   "on the written blocks + patch of the compacted matrix / fixed-width rows / dictionary / direction codes), then "
+                   "bdg_cheb_begin incl. its first launch; 'rebuilt' = the same with the copies rebuilt from scratch")
+    return out
+
+
 def pinned_h2d_peak(torch, local, nbytes=1 << 29):
     """Measured pinned-host -> device copy rate (GB/s): the roofline of the assembly (its inputs cross PCIe once)."""
     host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -525,6 +563,11 @@ def run_ours(args):
                "what": f"{calls} x [Hamiltonian.fill(pinned host arrays) + chebyshev_moments({2 * e2e_steps + 2}) -> host]; "
                        f"{e2e_steps} steps per call", "seconds": dt}
         system._sys.set_stream(B.stream.cuda_stream)
+
+    # ---- the reference's parameter-sweep idiom: re-enter `with` for some on-site terms, start the next recursion -------
+    incremental = None
+    if extras and rank == 0:
+        incremental = incremental_update_cost(b, system, scale, n_sites)
     del system
 
     # ---- less block repetition on the same lattice; the other BASELINE configs ----------------------
@@ -621,7 +664,7 @@ def run_ours(args):
                               else "three-term T_{n+1} = 2 H~ T_n - T_{n-1}")},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": head["gpu_launches"], "roofline": roofline,
         "parity_check": parity, "cpu_baseline": cpu, "block_repetition": repetition, "other_configs": others,
-        "strong_scaling": strong,
+        "strong_scaling": strong, "incremental_update": incremental,
     }
     emit(line)
     if world > 1:

@@ -22,6 +22,6 @@ __all__ = [
     "π", "σ", "σ0", "σ1", "σ2", "σ3", "jσ", "jσ0", "jσ1", "jσ2", "jσ3",
     "pi", "sigma", "sigma0", "sigma1", "sigma2", "sigma3",
     "jsigma", "jsigma0", "jsigma1", "jsigma2", "jsigma3",
-    # additions of this implementation
-    "AccuracyWarning", "Replicas", "release_cached",
 ]
+# Additions of this implementation are attributes of the package (bodge_b200.Replicas, .AccuracyWarning,
+# .release_cached) but stay out of __all__: `from bodge_b200 import *` gives exactly the reference's names.

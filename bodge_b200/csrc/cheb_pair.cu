@@ -212,7 +212,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //     a = <E_j, E_j>, c = <u, E_j>, b = <E_{j+1}, E_j>, d = <E_{j+1}, u>
 // from which the same four moments follow (cheb.cu: t2_normalize), but it moves THREE vector passes instead
 // of four, and two vector buffers suffice.  `first`: E_1 = T_2(H~) E_0 = 2 H~ u - E_0 (E_{-1} = E_1).
-template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE>
+//
+// REG (the 12-warp shape: one CTA per SM, 168 registers per thread): the warp's OWN records stay in registers from
+// plane to plane -- the T_n records it read as its x+1 neighbours are its centre records one iteration later and its x-1
+// neighbours (and the T_n of [B]) two iterations later, and the T_{n+1} records it computes are its own operands of [B]
+// for three iterations -- so shared memory is read only for what OTHER warps own: 6 instead of 16 LDS.128 per warp and
+// iteration.  The shared-memory / L1 data pipe is what bounds the 8-warp shape.
+template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE, bool REG = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
@@ -356,6 +362,15 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         }
         wait(0);
         wait(1);
+        double2 rt[S], rc[S], o1[S], o2[S];  // REG: own records of T_n planes i, i + 1 and of T_{n+1} planes i - 1, i - 2
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            rt[s] = rc[s] = o1[s] = o2[s] = make_double2(0.0, 0.0);
+            if (REG) {
+                rt[s] = lds_rec(aN + (cnt & (kRingN - 1)) * PLANE_N + (uint32_t)s * R);
+                rc[s] = lds_rec(aN + ((cnt + 1) & (kRingN - 1)) * PLANE_N + (uint32_t)s * R);
+            }
+        }
 
         for (int i = 0; i <= len + 1; ++i, pin_ += gstep, pout1 += gstep, pout2 += gstep) {
             const bool store = i >= 1 && i <= len;
@@ -395,6 +410,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             if (code_lane && i < len) jn2 = __ldg(dcode + cplane + coff);
             if (SELF) self_fragments<S>(jnext, fsN, table, lane);
             double2 tn[S] = {};  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
+            double2 out[S] = {};  // T_{n+1} of the warp's rows in the plane of [A]
             // [B]: update, store and dot products of row s from its product (yr, yi) and its own T_{n+1} record
             auto finish_b = [&](int s, double yr, double yi, const double2 &own1) {
                 const double2 t = tn[s];
@@ -421,11 +437,18 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t n0 = aN + ((c + 1) & (kRingN - 1)) * PLANE_N;
                 const uint32_t np = aN + ((c + 2) & (kRingN - 1)) * PLANE_N;
                 hold_fragments<DIAG, SELF, S>(jvA, jheld, keep, table, dtab, lane, self_lane);
-                double2 c_[S + 2], q[S], out[S];  // c_[1 + s] = the own record of site s; c_[0], c_[S + 1] = the warp's in-plane neighbours
+                double2 c_[S + 2], q[S];  // c_[1 + s] = the own record of site s; c_[0], c_[S + 1] = the warp's in-plane neighbours
+                if (REG) {
+                    c_[0] = lds_rec(n0 - R);
+                    c_[S + 1] = lds_rec(n0 + (uint32_t)S * R);
 #pragma unroll
-                for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(n0 + (uint32_t)(k - 1) * R);
+                    for (int s = 0; s < S; ++s) c_[1 + s] = rc[s], tn[s] = rt[s];
+                } else {
 #pragma unroll
-                for (int s = 0; s < S; ++s) tn[s] = lds_rec(nm + (uint32_t)s * R);
+                    for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(n0 + (uint32_t)(k - 1) * R);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) tn[s] = lds_rec(nm + (uint32_t)s * R);
+                }
 #pragma unroll
                 for (int s = 0; s < S; ++s) q[s] = lds_rec(np + (uint32_t)s * R);
                 const uint32_t t1 = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
@@ -436,6 +459,10 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                     if (MODE == 0) out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
                     else out[s] = make_double2(alpha * yr, alpha * yi);
                     sts_rec(t1 + (uint32_t)s * R, out[s]);
+                }
+                if (REG) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) rt[s] = rc[s], rc[s] = q[s];
                 }
                 if (store) {
 #pragma unroll
@@ -459,12 +486,19 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
                 hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
                 double2 c_[S + 2], m[S], q[S];
+                if (REG) {
+                    c_[0] = lds_rec(t0 - R);
+                    c_[S + 1] = lds_rec(t0 + (uint32_t)S * R);
 #pragma unroll
-                for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
+                    for (int s = 0; s < S; ++s) c_[1 + s] = o1[s], m[s] = o2[s], q[s] = out[s];
+                } else {
 #pragma unroll
-                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+                    for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                    for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                }
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
@@ -485,12 +519,17 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
                 hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
                 double2 own[S], m[S], q[S];
+                if (REG) {
 #pragma unroll
-                for (int s = 0; s < S; ++s) own[s] = lds_rec(t0 + (uint32_t)s * R);
+                    for (int s = 0; s < S; ++s) own[s] = o1[s], m[s] = o2[s], q[s] = out[s];
+                } else {
 #pragma unroll
-                for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+                    for (int s = 0; s < S; ++s) own[s] = lds_rec(t0 + (uint32_t)s * R);
 #pragma unroll
-                for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                    for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
+                }
                 RowSum<DIAG> r0, r1;
                 r0.begin(own[0], SELF ? fsB[0] : keep[0][0]);
                 r1.begin(own[1], SELF ? fsB[1] : keep[1][0]);
@@ -515,6 +554,10 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             }
             xphase ^= 1u;
 #endif
+            if (REG) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) o2[s] = o1[s], o1[s] = out[s];
+            }
             jvB = jvA;
             jvA = jnext;
             jnext = jn2;
@@ -608,13 +651,13 @@ pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ ci
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
                             double2 *, int, int, double, double, double, int, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S, int MINB> PairKernel pick_pair_shape(bool diag, bool self, bool t2) {
+template <int NW, int S, int MINB, bool REG = false> PairKernel pick_pair_shape(bool diag, bool self, bool t2) {
     if (self) {
-        if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1> : cheb_pair_step<false, true, NW, S, MINB, 1>;
-        return diag ? cheb_pair_step<true, true, NW, S, MINB, 0> : cheb_pair_step<false, true, NW, S, MINB, 0>;
+        if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1, REG> : cheb_pair_step<false, true, NW, S, MINB, 1, REG>;
+        return diag ? cheb_pair_step<true, true, NW, S, MINB, 0, REG> : cheb_pair_step<false, true, NW, S, MINB, 0, REG>;
     }
-    if (t2) return diag ? cheb_pair_step<true, false, NW, S, MINB, 1> : cheb_pair_step<false, false, NW, S, MINB, 1>;
-    return diag ? cheb_pair_step<true, false, NW, S, MINB, 0> : cheb_pair_step<false, false, NW, S, MINB, 0>;
+    if (t2) return diag ? cheb_pair_step<true, false, NW, S, MINB, 1, REG> : cheb_pair_step<false, false, NW, S, MINB, 1, REG>;
+    return diag ? cheb_pair_step<true, false, NW, S, MINB, 0, REG> : cheb_pair_step<false, false, NW, S, MINB, 0, REG>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -633,8 +676,11 @@ PairShape pair_shape(bool diag, bool self, bool t2) {
     // 8 warps x 2 sites: two CTAs per SM, one computes while the other waits at its barrier.  The shape
     // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
     // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
-    if (env_int("BDG_PAIR_WARPS", 8) <= 8)
+    const int warps = env_int("BDG_PAIR_WARPS", 8);
+    if (warps <= 8)
         s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2);
+    else if (warps <= 12)  // one CTA per SM, 168 registers: the warp's own records stay in registers (REG)
+        s.warps = 12, s.sites = 2, s.kernel = pick_pair_shape<12, 2, 1, true>(diag, self, t2);
     else
         s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2);
     const int W = s.warps * s.sites;

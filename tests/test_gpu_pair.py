@@ -73,7 +73,7 @@ SYSTEMS = {
 }
 
 # (BDG_PAIR_SEG, BDG_PAIR_P, BDG_PAIR_WARPS): None = planner's choice
-PLANS = [(None, None, None), (5, 7, None), (1, 1, None), (4, 30, 8), (3, 14, 8), (1000, 2, None)]
+PLANS = [(None, None, None), (5, 7, None), (1, 1, None), (4, 30, 8), (3, 14, 8), (1000, 2, None), (6, 22, 12), (2, 5, 12)]
 
 
 def _set_plan(monkeypatch, plan):
@@ -269,7 +269,7 @@ def test_two_step_kernels_on_random_shapes_and_plans(monkeypatch):
         scale = system.spectral_bound()
         plan = (int(rng.integers(1, Lx + 3)) if rng.random() < 0.7 else None,
                 int(rng.integers(1, 31)) if rng.random() < 0.7 else None,
-                16 if rng.random() < 0.3 else None)
+                (12 if rng.random() < 0.5 else 16) if rng.random() < 0.4 else None)
         _set_plan(monkeypatch, plan)
         n_cols, steps = int(rng.integers(1, 20)), int(rng.integers(1, 12))
         (cur, prev), fmt = _vectors(system._sys, "pair", n_cols, steps, scale)

@@ -179,3 +179,86 @@ def test_lanczos_coefficients_from_chebyshev_moments():
     assert ritz <= lam * (1 + 1e-6) and lam <= bound <= 1.15 * lam
     with pytest.raises(ValueError):
         kpm.jacobi_from_moments([0.0, 0.0])
+
+
+def test_c_dict_packer_equals_the_numpy_path(monkeypatch):
+    """csrc/pack_dict.c (one C loop over the dict) against the general numpy packing: same arrays, same order; anything
+    that is not the plain form (real matrix, broadcastable scalar, numpy integer coordinates) falls back or is handled."""
+    from bodge_b200.hamiltonian import _pack_entries
+
+    lat = b.CubicLattice((6, 5, 2))
+    entries = {}
+    for i in lat.sites():
+        entries[i, i] = 1.5 * b.σ0 - 0.1 * b.σ3
+    for i, j in lat.bonds():
+        entries[i, j] = -1.0 * b.σ0 + 0.2j * b.σ2
+    fast = _pack_entries(lat, entries)
+    assert _native._pack not in (None, False), "the C packer must have been built (bodge_b200.build.build_packer)"
+    monkeypatch.setattr(_native, "_pack", False)
+    slow = _pack_entries(lat, entries)
+    for a, c in zip(fast, slow):
+        assert a.dtype == c.dtype and np.array_equal(a, c)
+    monkeypatch.setattr(_native, "_pack", None)
+    # numpy integer coordinates go through __index__; a real-valued matrix makes the dict fall back as a whole
+    odd = {((np.int64(1), 2, 0), (1, 2, 0)): b.σ0, ((0, 0, 0), (0, 0, 1)): np.eye(2)}
+    i, j, v = _pack_entries(lat, odd)
+    assert list(i) == [lat.index((1, 2, 0)), 0] and list(j) == [lat.index((1, 2, 0)), 1] and v.dtype == np.complex128
+    with pytest.raises(TypeError):
+        _pack_entries(lat, {((0.5, 0, 0), (0, 0, 0)): b.σ0})      # float coordinates are refused, not truncated
+    with pytest.raises(ValueError):
+        _pack_entries(lat, {((9, 0, 0), (0, 0, 0)): b.σ0})        # out of bounds (reference: lattice.py:106)
+
+
+def test_index_arrays_are_range_checked():
+    assert _native._as_index(np.array([1, 2], dtype=np.int64)).dtype == np.int32
+    with pytest.raises(ValueError):
+        _native._as_index(np.array([2**31], dtype=np.int64))
+    with pytest.raises(TypeError):
+        _native._as_index(np.array([1.5]))
+
+
+def test_series_lengths_report_what_they_reach():
+    n, reached = kpm.free_energy_moments(0.1, 7.2)
+    assert reached == 1e-13 and abs(n - 30 * 7.2 / (np.pi * 0.1)) < 4
+    n, reached = kpm.free_energy_moments(1e-4, 7.2)        # the cap bites: the level reached is reported, not hidden
+    assert n == 32768 and 0.1 < reached < 1.0
+    n, reached = kpm.free_energy_moments(0.0, 7.2)
+    assert n == 8192 and reached == 1e-7
+    n, reached = kpm.ldos_moments(5.76, 0.003)
+    assert reached == 1e-13 and n == kpm.ldos_moments_needed(5.76, 0.003)
+    assert kpm.series_error(4096, 0.003 / 5.76) > 0.1     # the C3 example of VERDICT r1: 4096 moments are far too few
+
+
+def test_helpers_follow_the_reference_namespace():
+    from bodge_b200.hamiltonian import dwave, pwave, ssd, swave   # the reference exports them from bodge.hamiltonian
+
+    assert callable(swave()) and callable(dwave()) and callable(ssd)
+    f = pwave("np.sqrt(2) * abs(-1) * (p_x + jp_y) * e_z")       # numpy and builtins are in scope, as in the reference
+    g = b.pwave("(p_x + jp_y) * e_z")
+    assert np.allclose(f((0, 0, 0), (1, 0, 0)), np.sqrt(2) * g((0, 0, 0), (1, 0, 0)))
+
+
+def test_data_view_writes_through():
+    """``system._data[k, ...] = v`` (the reference's index() docstring idiom) must reach the device: the snapshot view
+    re-uploads on item assignment, also through a slice of it."""
+    from bodge_b200.hamiltonian import _DeviceData
+
+    class Sys:
+        def __init__(self):
+            self.uploads = []
+
+        def import_data(self, a):
+            self.uploads.append(np.array(a))
+
+    class Owner:
+        _scale_cache = 1.0
+        _sys = Sys()
+
+    owner = Owner()
+    view = _DeviceData(np.zeros((3, 4, 4), dtype=np.complex128), owner)
+    view[1, 0, 0] = 2.0
+    assert owner._sys.uploads[-1][1, 0, 0] == 2.0 and owner._scale_cache is None
+    sub = view[2]
+    sub[3, 3] = 5.0
+    assert owner._sys.uploads[-1][2, 3, 3] == 5.0 and owner._sys.uploads[-1].shape == (3, 4, 4)
+    assert isinstance(np.asarray(view), np.ndarray)
