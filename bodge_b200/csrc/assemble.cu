@@ -894,8 +894,11 @@ extern "C" int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const 
     }
     // Kernel-native copies first (the reference leaves the matrix modified when the Hermitian check raises, and so do
     // they): patch the blocks this call wrote, or mark everything stale.
+    // (Worth it for a part of the matrix only: one warp per written block costs more than the rebuild's streaming
+    // passes once a quarter of all blocks is rewritten.)
+    const bool partial = (n_hop + 2 * n_pair) * 4 <= m.n_blocks;
     {
-        bool ok = sys->packed_valid && sys->ell.valid;
+        bool ok = partial && sys->packed_valid && sys->ell.valid;
         if (ok && n_hop) BDG_TRY(ell_patch(sys, n_hop, sh[3].as<int32_t>(), &ok));
         if (ok && n_pair) BDG_TRY(ell_patch(sys, n_pair, sp[3].as<int32_t>(), &ok));
         if (ok && n_pair) BDG_TRY(ell_patch(sys, n_pair, sp[4].as<int32_t>(), &ok));
@@ -904,7 +907,7 @@ extern "C" int bdg_scatter(bdg_t *sys, int64_t n_hop, const int32_t *h_i, const 
     }
     if (herm_tol >= 0.0) {
         double dev = 0.0;
-        if (was_verified && herm_tol >= sys->herm_tol) {
+        if (partial && was_verified && herm_tol >= sys->herm_tol) {
             // everything else passed this tolerance before and has not changed: look at the written blocks only
             h->max_bits = 0ull;
             BDG_CUDA(cudaMemcpyAsync(&d->max_bits, &h->max_bits, sizeof(unsigned long long), cudaMemcpyHostToDevice, sys->stream));

@@ -91,8 +91,9 @@ int bdg_clear(bdg_t *sys);
 /* Incremental updates (the reference's parameter-sweep idiom: re-enter `with` for a few keys, ask for an observable
  * again -- tests/test_physics.py:155-160, 221-224; its scatter touches only the keys set, bodge/hamiltonian.py:102-118).
  * bdg_scatter patches the compacted matrix and the step kernels' own copies of it (fixed-width rows, block dictionary,
- * direction codes) for the blocks it writes, and checks Hermiticity on those blocks only, whenever the zero pattern is
- * unchanged and the stored matrix had passed the check before; otherwise the copies are rebuilt by the next recursion.
+ * direction codes) for the blocks it writes, and checks Hermiticity on those blocks only, whenever it rewrites at most a
+ * quarter of the blocks, the zero pattern is unchanged and the stored matrix had passed the check before; otherwise the
+ * copies are rebuilt by the next recursion.
  * out[0] = compactions (eliminate_zeros) so far, out[1] = builds of the kernel-native copies, out[2] = scatters that
  * were patched in place, out[3] = blocks patched, out[4] = Hermitian checks restricted to the written blocks. */
 int bdg_stats(bdg_t *sys, int64_t out[5]);
