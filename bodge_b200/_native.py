@@ -109,10 +109,20 @@ def pack_dict(entries: dict, keys: np.ndarray, vals: np.ndarray) -> int:
             lib = C.PyDLL(path)
             lib.bdg_pack_dict.argtypes = [C.py_object, _vp, _vp]
             lib.bdg_pack_dict.restype = C.c_longlong
+            lib.bdg_pack_dict_cubic.argtypes = [C.py_object, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _vp]
+            lib.bdg_pack_dict_cubic.restype = C.c_longlong
             _pack = lib
     if _pack is False:
         return -1
     return int(_pack.bdg_pack_dict(entries, keys.ctypes.data_as(_vp), vals.ctypes.data_as(_vp)))
+
+
+def pack_dict_cubic(entries: dict, shape, site_i: np.ndarray, site_j: np.ndarray, vals: np.ndarray) -> int:
+    """``pack_dict`` for a stock ``CubicLattice(shape)``: the keys become flat int32 site indices in the same C loop."""
+    if pack_dict({}, np.empty((0, 2, 3), np.int64), np.empty((0, 2, 2), np.complex128)) < 0:
+        return -1
+    return int(_pack.bdg_pack_dict_cubic(entries, int(shape[0]), int(shape[1]), int(shape[2]), site_i.ctypes.data_as(_vp),
+                                         site_j.ctypes.data_as(_vp), vals.ctypes.data_as(_vp)))
 
 
 def last_error() -> str:

@@ -63,8 +63,12 @@ def _pack_entries(lattice: Lattice, entries: dict):
         return none, none.copy(), np.zeros((0, 2, 2), dtype=np.complex128)
     # Fast path: one C loop over the dict (csrc/pack_dict.c) when every entry has the plain form the reference's
     # own examples use -- integer coordinate tuples and 2x2 complex128 arrays.
-    keys = np.empty((n, 2, 3), dtype=np.int64)
     vals = np.empty((n, 2, 2), dtype=np.complex128)
+    if type(lattice) is CubicLattice and lattice.size < 2**31:  # stock lattice: flat indices in the same loop
+        i, j = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        if _native.pack_dict_cubic(entries, lattice.shape, i, j, vals) == n:
+            return i, j, vals
+    keys = np.empty((n, 2, 3), dtype=np.int64)
     if _native.pack_dict(entries, keys, vals) != n:
         try:
             keys = np.array(list(entries.keys()))

@@ -196,8 +196,15 @@ def test_c_dict_packer_equals_the_numpy_path(monkeypatch):
     assert _native._pack not in (None, False), "the C packer must have been built (bodge_b200.build.build_packer)"
     monkeypatch.setattr(_native, "_pack", False)
     slow = _pack_entries(lat, entries)
-    for a, c in zip(fast, slow):
-        assert a.dtype == c.dtype and np.array_equal(a, c)
+    for a, c in zip(fast, slow):  # (the cubic fast path hands out int32 site indices, the general one int64)
+        assert a.dtype.kind == c.dtype.kind and np.array_equal(a, c)
+    # a non-stock lattice goes through the generic key packer + its own index()
+    class Shifted(b.CubicLattice):
+        pass
+
+    other = _pack_entries(Shifted((6, 5, 2)), entries)
+    for a, c in zip(other, slow):
+        assert np.array_equal(a, c)
     monkeypatch.setattr(_native, "_pack", None)
     # numpy integer coordinates go through __index__; a real-valued matrix makes the dict fall back as a whole
     odd = {((np.int64(1), 2, 0), (1, 2, 0)): b.σ0, ((0, 0, 0), (0, 0, 1)): np.eye(2)}
