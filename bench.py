@@ -306,7 +306,8 @@ class Bench:
                          scale=scale, kernel=kernel)
         s.cheb_reserve(W + 2 * K + 8)
         s.cheb_steps(W)
-        # pilot: K steps, to size the timed region
+        launches_before_pilot = s.cheb_info()["launches"]
+        # pilot: K steps, to size the timed region (and, the GPU still cool, the kernel at burst clocks)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         p0.record(self.stream)
@@ -314,6 +315,7 @@ class Bench:
         p1.record(self.stream)
         torch.cuda.synchronize()
         pilot_ms = self.max_over_ranks([p0.elapsed_time(p1)])[0]
+        pilot_launches = s.cheb_info()["launches"]
         R = max(1, int(math.ceil(min_s * 1e3 / max(pilot_ms, 1e-3))))
         s.cheb_reserve(R * K + 8)
         info, fmt = s.cheb_info(), s.cheb_format()
@@ -346,7 +348,8 @@ class Bench:
                 "ms_per_step": total_ms / steps, "kernel_ms_per_step": kernel_ms / steps,
                 "steps_per_launch": steps / max(step_launches, 1), "bytes_per_step": info["bytes_per_step"],
                 "moved_bytes_per_step": moved_step, "distinct_blocks": fmt["distinct_blocks"], "n_blocks": info["n_blocks"],
-                "panel_width": info["panel_width"], "mu": mu_dev[:n_mom] if reduce_moments else None, "scale": scale}
+                "panel_width": info["panel_width"], "mu": mu_dev[:n_mom] if reduce_moments else None, "scale": scale,
+                "pilot_ms": pilot_ms, "pilot_steps": K, "pilot_launches": pilot_launches - launches_before_pilot}
 
     def summary(self, t, cfg_key, cols, *, jobs):
         """Compact record of a `timed()` result: throughput + the physical roofline fraction."""
@@ -631,6 +634,15 @@ def run_ours(args):
                         "speedup_vs_one_pass_roofline: > 1 because the block dictionary takes the matrix out of the stream and the "
                         "even-vector recursion moves three vector passes per TWO steps",
                 "assembly": assembly}
+    # the same kernel in the K pilot steps right after the warm-up, before the power cap pulls the SM clock down
+    burst_launch_ms = head["pilot_ms"] / max(head["pilot_launches"], 1)
+    phys_launch = roofline["traffic"] or hs["moved_bytes_per_launch"]
+    roofline["burst"] = {"steps": head["pilot_steps"], "kernel_ms_per_launch": burst_launch_ms,
+                         "steps_per_s": jobs * head["pilot_steps"] / (head["pilot_ms"] * 1e-3),
+                         "achieved_GBps": phys_launch / (burst_launch_ms * 1e-3) / 1e9,
+                         "frac": phys_launch / (burst_launch_ms * 1e-3) / 1e9 / B.peak,
+                         "what": "the K pilot steps that size the timed region (GPU still cool); frac above is the sustained figure of "
+                                 "the >= 1 s region, see `clocks`"}
     if three_term:
         roofline["three_term_recursion"] = three_term
     if plain is not None:

@@ -444,20 +444,10 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                     for (int s = 0; s < S; ++s) c_[1 + s] = rc[s], tn[s] = rt[s];
                 } else {
-#ifdef BDG_PAIR_ABLATE_OWN_LDS  // timing experiment (wrong numbers): what would it buy if the own records cost no shared-memory read?
-                    c_[0] = lds_rec(n0 - R);
-                    c_[S + 1] = lds_rec(n0 + (uint32_t)S * R);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        c_[1 + s] = make_double2(c_[0].x + 1.0 * s, c_[S + 1].y);
-                        tn[s] = make_double2(c_[S + 1].x, c_[0].y - 1.0 * s);
-                    }
-#else
 #pragma unroll
                     for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(n0 + (uint32_t)(k - 1) * R);
 #pragma unroll
                     for (int s = 0; s < S; ++s) tn[s] = lds_rec(nm + (uint32_t)s * R);
-#endif
                 }
 #pragma unroll
                 for (int s = 0; s < S; ++s) q[s] = lds_rec(np + (uint32_t)s * R);
@@ -502,23 +492,12 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                     for (int s = 0; s < S; ++s) c_[1 + s] = o1[s], m[s] = o2[s], q[s] = out[s];
                 } else {
-#ifdef BDG_PAIR_ABLATE_OWN_LDS
-                    c_[0] = lds_rec(t0 - R);
-                    c_[S + 1] = lds_rec(t0 + (uint32_t)S * R);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        c_[1 + s] = make_double2(c_[0].x + out[s].y, c_[S + 1].y);
-                        m[s] = make_double2(c_[S + 1].x, c_[0].y - out[s].x);
-                        q[s] = out[s];
-                    }
-#else
 #pragma unroll
                     for (int k = 0; k < S + 2; ++k) c_[k] = lds_rec(t0 + (uint32_t)(k - 1) * R);
 #pragma unroll
                     for (int s = 0; s < S; ++s) m[s] = lds_rec(tm + (uint32_t)s * R);
 #pragma unroll
                     for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
-#endif
                 }
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
