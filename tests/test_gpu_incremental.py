@@ -100,8 +100,9 @@ def test_patched_copies_equal_a_rebuild(gpu_api, tag):
     for kernel in kernels:  # same matrix, same arithmetic: the patched copies give bit-identical moments
         assert np.array_equal(got[kernel], want[kernel]), kernel
 
-    # (2) half of all sites get ONE common new on-site block and gap (the spin-valve sweep of the reference's tests)
-    half = [s for s in lattice.sites() if s[0] < shape[0] // 2]
+    # (2) a quarter of all sites get ONE common new on-site block and gap (the spin-valve sweep of the reference's tests;
+    # an update that rewrites more than a quarter of all BLOCKS takes the rebuild path by design: step 6)
+    half = [s for s in lattice.sites() if s[0] < max(1, shape[0] // 4)]
     blocks.append(_onsite(half, lattice, [3.0 * σ0 + 0.4 * σ3] * len(half), pair=[-0.25 * jσ2] * len(half)))
     system.fill(*blocks[-1])
     got = _check(system, blocks, shape, kernels)
@@ -131,6 +132,14 @@ def test_patched_copies_equal_a_rebuild(gpu_api, tag):
                    np.array([hop, hop.conj().T]), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2, 2), np.complex128)))
     system.fill(*blocks[-1])
     _check(system, blocks, shape, [k for k in kernels if k not in ("dict_diag",)])
+
+    # (6) rewriting the whole Hamiltonian in one block: streaming rebuild instead of one warp per block
+    before = system._sys.stats()
+    system.fill(*blocks[0])
+    blocks.append(blocks[0])
+    _check(system, blocks, shape, [k for k in kernels if k not in ("dict_diag",)])
+    after = system._sys.stats()
+    assert after["patched_scatters"] == before["patched_scatters"] and after["native_builds"] == before["native_builds"] + 1, after
 
 
 def test_dict_api_sweep_stays_incremental(gpu_api):
