@@ -8,19 +8,20 @@
 // it is consumed out of shared memory.  With the matrix already out of the HBM stream (dictionary
 // format) that is the only way past the one-pass roofline of the step.
 //
-// Geometry.  Lattices whose x-planes are one-dimensional (Lz = 1 or Ly = 1; M = sites per plane).
-// The plane is cut into patches of P owned sites; a CTA marches one patch along a segment of x:
+// Geometry.  Lattices whose x-planes are one-dimensional (Lz = 1 or Ly = 1; M >= 3 sites per plane, Lx >= 3 planes),
+// treated as a TORUS: open and periodic stencils run the same code, the matrix (direction codes) decides what is
+// connected.  The plane is cut into patches of P owned sites; a CTA marches one patch along a segment of x:
 //
-//   iteration x:  [A] T_{n+1}(x, y) for the P owned sites AND one halo site on either side, from
-//                     T_n planes x-1, x, x+1 (P + 4 sites each), staged in a shared-memory ring of 8
-//                     planes by bulk async copies (TMA: cp.async.bulk, one contiguous 9 KB run per
-//                     plane, five planes ahead, completion on an mbarrier), and T_{n-1}(x, y), which
-//                     only this warp reads: straight to registers, one plane ahead;
-//                     the result goes to a shared-memory ring (4 planes) and, for owned sites of
-//                     owned planes, to HBM;
-//                 __syncthreads
-//                 [B] T_{n+2}(x-1, y) for the owned sites from the T_{n+1} ring's planes x-2, x-1, x
-//                     (T_n(x-1, y) is still in the T_n ring).
+//   iteration i:  [A] T_{n+1} of plane x0 - 1 + i for the P owned sites AND one halo site on either side, from three
+//                     T_n planes (P + 4 sites each) staged in a shared-memory ring of 8 planes by bulk async copies
+//                     (TMA: cp.async.bulk, one contiguous 9 KB run per plane -- plus one small run from the opposite
+//                     side of the plane for the first / last patch --, seven planes ahead, completion on an mbarrier),
+//                     and T_{n-1} of the warp's rows, which only this warp reads: straight to registers, one plane
+//                     ahead; the result goes to a shared-memory ring (4 planes) and, for owned sites of owned planes,
+//                     to HBM;
+//                 __syncthreads; the plane [A] no longer needs is replaced by the plane eight ahead
+//                 [B] T_{n+2} of the plane one behind, for the owned sites, from the T_{n+1} ring's three planes and the
+//                     T_n records [A] read as its x-1 neighbours (kept in registers across the barrier).
 //
 // The halo T_{n+1} values (one site either side in y, one plane either side of the segment in x)
 // are recomputed, not exchanged: (P+2)/P x (len+2)/len redundant work on sub-step [A], no
@@ -29,8 +30,15 @@
 // buffers (four vector buffers in rotation) instead of in place.
 //
 // Arithmetic per row is exactly that of cheb_step_ell<.., DICT, DIAG> (same fragments, same order,
-// same update expression): the vectors are bit-identical to the single-step dictionary kernels';
-// the dot products are summed over a different partition of the rows (agree to rounding).
+// same update expression): on open lattices the vectors are bit-identical to the single-step dictionary kernels'
+// (where a neighbour wraps around, the terms of a row are added in stencil direction here and in ascending block
+// column there: equal to rounding); the dot products are summed over a different partition of the rows (agree to
+// rounding).
+//
+// Compile-time experiments kept for the record (all within +-1 % of the default at 10^6 sites):
+// -DBDG_PAIR_PV3 (E_{j-1} two planes ahead), -DBDG_PAIR_SPLIT (split-phase mbarrier hand-over between [A] and [B],
+// [B] started on the warp's own records before the wait); run time: BDG_PAIR_WARPS=12 (REG: own records in registers,
+// one CTA per SM), =16; BDG_PAIR_SELF, BDG_PAIR_P, BDG_PAIR_SEG.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
