@@ -608,6 +608,10 @@ def run_ours(args):
         t = B.timed(sysx, hi - lo, args.kernel, K, W, min_s=0.3, probe_rows=rows[lo:hi], reduce_moments=False)
         others["C3"] = B.summary(t, "C3", hi - lo, jobs=1)
         others["C3"]["what"] = "4096 probe columns (1024 sites x 4) sharded over the GPUs: steps/s of the whole LDOS job"
+        if world == 1:  # BASELINE shards C3 over 2/4/8 GPUs: one GPU's share of the 8-GPU run (512 columns) beside the whole job
+            t8 = B.timed(sysx, 512, args.kernel, K, W, min_s=0.3, probe_rows=rows[:512], reduce_moments=False)
+            others["C3_share_of_8"] = B.summary(t8, "C3", 512, jobs=1)
+            others["C3_share_of_8"]["what"] = "the 512 probe columns one GPU holds when C3 is sharded over 8 GPUs (SURVEY 8d)"
         # the exchange of this path: all-gather of the per-column moments (column order = rank order), checked
         if world > 1:
             mine = torch.from_numpy(sysx._sys.cheb_read(8, hi - lo)).to(B.dev)
