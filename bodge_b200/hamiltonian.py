@@ -406,6 +406,12 @@ class Hamiltonian:
 
         read.leading_dim = 1
         if vectors is None:
+            if self.shape[0] > (1 << 18):
+                # the reference's exact path (dense eigvalsh) stops being possible long before this size; the exact KPM
+                # trace still works but is O(N^2): say so instead of silently running for hours
+                warnings.warn(f"free_energy(cuda=True) without vectors= takes the exact trace over all {self.shape[0]} unit "
+                              "columns (O(N^2) work); pass vectors=64 or so for a stochastic estimate (relative error "
+                              "~ 1/sqrt(vectors * 4N))", AccuracyWarning, stacklevel=2)
             total = self._columns(n_mom, read, True, rows=np.arange(self.shape[0]), scale=scale, kernel=kernel)
             return float(total[0])
         total = self._columns(n_mom, read, True, vectors=vectors, seed=seed, scale=scale, kernel=kernel)
