@@ -411,7 +411,6 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                     if (i <= len) pvn[s] = ld_prev(ta + ((size_t)xprev * wk.M + yw[s]) * 32 + lane);
                 }
             }
-            wait(i + 2);
             int jn2 = -1;
             cplane += plane_codes;
             cplane -= cplane >= all_codes ? all_codes : 0;
@@ -457,13 +456,26 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                     for (int s = 0; s < S; ++s) tn[s] = lds_rec(nm + (uint32_t)s * R);
                 }
+                const uint32_t t1 = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
+                // The newest plane (x+1 neighbours) feeds the LAST term of a row: its barrier is waited for only after the
+                // other four terms are under way (+1 %: profiles/r02/21_latewait.log).
+                RowSum<DIAG> rs[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    rs[s].begin(c_[1 + s], SELF ? fsA[s] : keep[s][0]);
+                    rs[s].add(tn[s], keep[s][1]);
+                    rs[s].add(c_[s], keep[s][2]);
+                    rs[s].add(c_[2 + s], keep[s][3]);
+                }
+                wait(i + 2);
 #pragma unroll
                 for (int s = 0; s < S; ++s) q[s] = lds_rec(np + (uint32_t)s * R);
-                const uint32_t t1 = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
-                    row_product<DIAG>(c_[1 + s], tn[s], c_[s], c_[2 + s], q[s], SELF ? fsA[s] : keep[s][0], keep[s], yr, yi);
+                    rs[s].add(q[s], keep[s][4]);
+                    rs[s].end();
+                    yr = rs[s].yr, yi = rs[s].yi;
                     if (MODE == 0) out[s] = make_double2(fma(alpha, yr, -pv[s].x), fma(alpha, yi, -pv[s].y));
                     else out[s] = make_double2(alpha * yr, alpha * yi);
                     sts_rec(t1 + (uint32_t)s * R, out[s]);
