@@ -582,7 +582,7 @@ def run_ours(args):
     repetition = others = None
     if extras:
         repetition = {}
-        for key in ("C5_disordered", "C5_random"):
+        for key in ("C5_disordered", "C5_random", "C5_periodic"):
             try:
                 sysx = B.build(key)
                 t = B.timed(sysx, cols, args.kernel, K, W, min_s=0.5)

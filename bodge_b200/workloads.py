@@ -75,8 +75,15 @@ def dwave_rashba(shape, mu=-0.5, alpha=0.2, dd=0.1, t=1.0):
     return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
 
 
-def junction(shape, mu=-3.0, d0=0.2, phi=np.pi / 2, m=0.3, t=1.0):
-    """C5: superconductor / altermagnet / superconductor Josephson junction along x."""
+def _edges(lattice: CubicLattice, axis: int):
+    """Directed periodic-edge pairs along ``axis`` (opposite faces, bodge/lattice.py:161-197): (i -> j) then (j -> i)."""
+    i, j = lattice.edges_array(axis)
+    return np.concatenate([i, j]), np.concatenate([j, i])
+
+
+def junction(shape, mu=-3.0, d0=0.2, phi=np.pi / 2, m=0.3, t=1.0, periodic=False):
+    """C5: superconductor / altermagnet / superconductor Josephson junction along x.  ``periodic``: the reference's
+    periodic edges filled in with ``-t σ0`` along both in-plane axes (a torus; the junction then closes on itself)."""
     lat = CubicLattice(shape)
     n = lat.size
     Lx, Ly, Lz = shape
@@ -99,6 +106,13 @@ def junction(shape, mu=-3.0, d0=0.2, phi=np.pi / 2, m=0.3, t=1.0):
         h_i.append(i)
         h_j.append(j)
         h_val.append(vals)
+    if periodic:
+        for axis in (2, 1, 0):
+            if shape[axis] >= 3:
+                i, j = _edges(lat, axis)
+                h_i.append(i)
+                h_j.append(j)
+                h_val.append(_tile(-t * σ0, len(i)))
     return _finish(h_i, h_j, h_val, p_i, p_j, p_val)
 
 
@@ -191,6 +205,8 @@ CONFIGS = {
                           label="CubicLattice((1000,1000,1)) s-wave with site-disordered potential and gap (10^6 distinct on-site blocks)"),
     "C5_random": dict(shape=(1000, 1000, 1), build=random_blocks,
                       label="CubicLattice((1000,1000,1)) every block distinct (random on-site terms and random Hermitian hopping)"),
+    "C5_periodic": dict(shape=(1000, 1000, 1), build=lambda shape: junction(shape, periodic=True),
+                        label="CubicLattice((1000,1000,1)) junction on a torus (the reference's periodic edges filled in)"),
     "C5_bilayer": dict(shape=(1024, 1024, 1), build=benchmark_bilayer,
                        label="CubicLattice((1024,1024,1)) S/F bilayer with phase winding (the reference's misc/benchmark.py model)"),
 }

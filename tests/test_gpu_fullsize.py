@@ -46,7 +46,7 @@ def full(request):
     cache.clear()
 
 
-@pytest.mark.parametrize("key", ["C5", "C4", "C5_disordered", "C5_random"])
+@pytest.mark.parametrize("key", ["C5", "C4", "C5_disordered", "C5_random", "C5_periodic"])
 def test_full_size_assembly_equals_the_oracle(full, key):
     system, (ptr, idx, dat), scale, _ = full(key)
     got_ptr, got_idx, got_dat = system._sys.export_bsr(True)
@@ -61,6 +61,7 @@ def test_full_size_assembly_equals_the_oracle(full, key):
     ("C4", ["auto", "dict", "ell", "dmma"]),
     ("C5_disordered", ["auto", "pair", "dict_diag", "ell"]),
     ("C5_random", ["auto", "dmma"]),
+    ("C5_periodic", ["auto", "pair", "dict_diag", "ell"]),   # wrap-around halos of 72 patches x 4 segments at full size
 ])
 def test_full_size_moments_equal_the_oracle(full, key, kernels):
     system, _, scale, want = full(key)
@@ -75,6 +76,8 @@ def test_full_size_moments_equal_the_oracle(full, key, kernels):
         assert {"t2", "pair", "dict_diag", "dict", "ell", "dmma"} <= seen
     if key == "C5_random":
         assert "ell" in seen  # nothing repeats: the matrix is streamed
+    if key == "C5_periodic":
+        assert {"t2", "pair"} <= seen  # the periodic stencil runs the two-step kernels
 
 
 def test_C2_256_columns_equal_the_oracle():
