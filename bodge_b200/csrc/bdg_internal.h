@@ -83,6 +83,14 @@ struct PairWalk {
     int seg_len = 1, n_segs = 1, n_items = 1;
 };
 
+// Item grid of the two-applications-per-pass kernel for three-dimensional lattices (cheb_cube.cu): the (y, z) plane
+// is cut into nPy x nPz patches; an item = (patch, segment of seg_len consecutive x), handed out segment-major.
+struct CubeWalk {
+    int Lx = 1, Ly = 1, Lz = 1;
+    int nPy = 1, nPz = 1, n_patches = 1;
+    int seg_len = 1, n_segs = 1, n_items = 1;
+};
+
 // ---- Chebyshev state ----------------------------------------------------------------------
 struct ChebState {
     bool active = false;
@@ -103,6 +111,9 @@ struct ChebState {
     int t2_rows_normalized = 0;  // launches whose dot rows have been rewritten in the single-step format
     int pair_grid_x = 0;
     PairWalk pair_walk;
+    bool cube = false;         // t2 on a three-dimensional lattice: cheb_cube.cu (4-column panels)
+    int cube_shape = 0;        // which patch shape of cheb_cube.cu
+    CubeWalk cube_walk;
     // dots[(step * 2 + which) * n_panels * PW + panel * PW + c]; which 0 = <T_n,T_n>, 1 = <T_{n+1},T_n>
     DevBuf dots;
     DevBuf partials;  // per-CTA partial dot products of the step in flight
@@ -140,6 +151,9 @@ struct EllDev {
     bool pair_usable = false;
     int pair_M = 0;
     DevBuf dcode;  // int32 [n_sites][5]: dictionary code per stencil direction (self, x-1, y-1, y+1, x+1), -1 = none
+    // ... and its three-dimensional sibling (cheb_cube.cu): open nearest-neighbour stencil on a lattice with Ly, Lz >= 2.
+    bool cube_usable = false;
+    DevBuf dcode3;  // int32 [n_sites][8]: (self, x-1, y-1, z-1, z+1, y+1, x+1, pad); -1 = no block, -2 = no site in y / z
     DevBuf tmp_keys, tmp_rep, tmp_where, tmp_dense;  // hash-table scratch of the dictionary build (kept for rebuilds)
     // ... and what stays alive for incremental updates (ell_patch): the hash table itself (tmp_keys, `hash_cap` slots),
     // posid[hash position] = dictionary code (-1: unused), the table's capacity in entries, device counters
@@ -208,5 +222,10 @@ int pair_configure(bdg_system *sys);  // patch / segment plan and grid for the c
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step);
 int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
 bool pair_streams_onsite(const bdg_system *sys);  // on-site fragments fetched per row (large dictionaries) instead of held
+
+// cheb_cube.cu
+int cube_probe(bdg_system *sys);      // sets sys->ell.cube_usable / dcode3 (called by ell_build)
+int cube_configure(bdg_system *sys);  // patch shape / segment plan and grid for the current ChebState
+int cube_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double *dots_step);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

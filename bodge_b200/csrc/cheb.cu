@@ -427,6 +427,11 @@ bool auto_pair_enabled() {
     const char *v = getenv("BDG_AUTO_PAIR");
     return v && *v ? atoi(v) != 0 : kAutoPairDefault;
 }
+// ... and, for callers that only read moments, the even-vector recursion on three-dimensional lattices (BDG_AUTO_CUBE=0: off)
+bool auto_cube_enabled() {
+    const char *v = getenv("BDG_AUTO_CUBE");
+    return v && *v ? atoi(v) != 0 : true;
+}
 
 int launch_step(bdg_system *sys, bool first) {
     ChebState &st = sys->cheb;
@@ -540,7 +545,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     BDG_REQUIRE(kind != BDG_X0_PROBE || probe_rows != nullptr, "probe rows missing");
     BDG_REQUIRE(kernel >= BDG_KERNEL_AUTO && kernel <= BDG_KERNEL_AUTO_MOMENTS, "unknown kernel %d", kernel);
     BDG_TRY(build_packed(sys));
-    bool pair = false, t2 = false;
+    bool pair = false, t2 = false, cube = false;
     if (kernel == BDG_KERNEL_AUTO || kernel == BDG_KERNEL_ELL || kernel == BDG_KERNEL_DICT || kernel == BDG_KERNEL_DICT_DIAG ||
         kernel == BDG_KERNEL_PAIR || kernel == BDG_KERNEL_T2 || kernel == BDG_KERNEL_AUTO_MOMENTS) {
         BDG_TRY(ell_build(sys));
@@ -552,13 +557,21 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
         // cost more bytes than the fusion saves, so narrow panels stay on the single-step kernels there.
         const bool small = sys->ell.n_sites <= (1 << 16);
         const bool pair_ok = sys->ell.pair_usable && (n_cols >= 5 || small);
-        BDG_REQUIRE((kernel != BDG_KERNEL_PAIR && kernel != BDG_KERNEL_T2) || pair_ok,
-                    "the two-steps-per-pass kernels need >= 5 columns (any number on lattices of <= 65536 sites) and a block "
-                    "dictionary on a lattice with one-dimensional x-planes and an open nearest-neighbour stencil");
+        // Three-dimensional lattices: the even-vector recursion on 4-column panels (cheb_cube.cu): open stencil,
+        // real-diagonal hopping blocks, few distinct blocks (its fragments are held in registers).
+        const bool cube_ok = sys->ell.cube_usable && sys->ell.n_unique <= 64 && (n_cols >= 3 || small);
+        BDG_REQUIRE(kernel != BDG_KERNEL_PAIR || pair_ok,
+                    "the two-steps-per-pass kernel needs >= 5 columns (any number on lattices of <= 65536 sites) and a block "
+                    "dictionary on a lattice with one-dimensional x-planes and a nearest-neighbour stencil");
+        BDG_REQUIRE(kernel != BDG_KERNEL_T2 || pair_ok || cube_ok,
+                    "the even-vector recursion needs a block dictionary on a lattice with a nearest-neighbour stencil: one-dimensional "
+                    "x-planes and >= 5 columns, or a three-dimensional open lattice with real-diagonal hopping blocks, <= 64 "
+                    "distinct blocks and >= 3 columns (any number of columns on lattices of <= 65536 sites)");
         const bool prefer = pair_ok && sys->ell.diag_usable && auto_pair_enabled();
         // Callers that only read moments / observables get the even-vector recursion (three vector passes per
         // two steps); callers that step and look at T_n, T_{n-1} the pair kernel (four).
-        t2 = kernel == BDG_KERNEL_T2 || (kernel == BDG_KERNEL_AUTO_MOMENTS && prefer);
+        t2 = kernel == BDG_KERNEL_T2 || (kernel == BDG_KERNEL_AUTO_MOMENTS && (prefer || (cube_ok && auto_cube_enabled())));
+        cube = t2 && !pair_ok && cube_ok;
         pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && prefer);
         if (kernel == BDG_KERNEL_PAIR || kernel == BDG_KERNEL_T2 || kernel == BDG_KERNEL_AUTO_MOMENTS) kernel = BDG_KERNEL_AUTO;
         BDG_REQUIRE(kernel != BDG_KERNEL_ELL || sys->ell.usable,
@@ -584,7 +597,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     st.active = false;
     st.kernel = kernel;
     st.n_cols = n_cols;
-    st.panel_width = (n_cols >= 5 || pair || t2) ? 8 : (n_cols >= 3 ? 4 : n_cols);
+    st.panel_width = cube ? 4 : (n_cols >= 5 || pair || t2) ? 8 : (n_cols >= 3 ? 4 : n_cols);
     st.n_panels = (int)ceil_div(n_cols, st.panel_width);
     st.scale = scale;
     st.steps_done = 0;
@@ -592,6 +605,7 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     st.prev = 1;
     st.pair = pair;
     st.t2 = t2;
+    st.cube = cube;
     st.t2_rows_normalized = 0;
     st.dot_capacity = (int)(st.dots.bytes / ((size_t)2 * st.n_panels * st.panel_width * sizeof(double)));
 
@@ -613,7 +627,8 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
     }
 
     st.pair_grid_x = 0;
-    if (st.pair || st.t2) BDG_TRY(pair_configure(sys));
+    if (st.cube) BDG_TRY(cube_configure(sys));
+    else if (st.pair || st.t2) BDG_TRY(pair_configure(sys));
 
     const size_t vec_elems = (size_t)st.n_panels * n * st.panel_width * 4;
     for (int b = 0; b < (st.pair ? 4 : 2); ++b) BDG_TRY(dev_alloc(sys, st.vec[b], vec_elems * sizeof(double2)));
@@ -794,7 +809,9 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
     if (kernel) *kernel = st.t2 ? BDG_KERNEL_T2 : st.pair ? BDG_KERNEL_PAIR : st.kernel;
     if (n_distinct_blocks) *n_distinct_blocks = e.valid ? e.n_unique : 0;
     if (matrix_bytes_per_step) {
-        if (st.pair || st.t2)  // one pass over the codes (and, site-dependent on-site blocks: over those) serves two steps
+        if (st.cube)  // eight 4-byte codes per site, read once per panel and launch (= two steps)
+            *matrix_bytes_per_step = e.n_sites * 32 * st.n_panels / 2 + e.n_unique * 256;
+        else if (st.pair || st.t2)  // one pass over the codes (and, site-dependent on-site blocks: over those) serves two steps
             *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + (pair_streams_onsite(sys) ? std::min(e.n_unique, e.n_sites) * 256 / 2 : e.n_unique * 256);
         else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;

@@ -410,6 +410,8 @@ struct PatchArgs {
     int table_cap, diag_required;
     int32_t *dcode;
     int Lx, M;
+    int32_t *dcode3;
+    int Ly, Lz;
     int *status;
 };
 
@@ -506,6 +508,10 @@ patch_blocks(int64_t n, const int32_t *__restrict__ klist, const PatchArgs a) {
         if (a.dcode) {
             const int dir = u == 0 ? 0 : torus_direction(row, col, a.Lx, a.M);
             if (dir >= 0) a.dcode[(size_t)row * 5 + dir] = id;
+        }
+        if (a.dcode3) {
+            const int dir = u == 0 ? 0 : cube_direction(row, col, a.Ly, a.Lz);
+            if (dir >= 0) a.dcode3[(size_t)row * 8 + dir] = id;
         }
     }
 }
@@ -676,6 +682,7 @@ void ell_release(bdg_system *sys) {
     dev_free(sys, sys->ell.table);
     dev_free(sys, sys->ell.dtab);
     dev_free(sys, sys->ell.dcode);
+    dev_free(sys, sys->ell.dcode3);
     dev_free(sys, sys->ell.tmp_keys);
     dev_free(sys, sys->ell.tmp_rep);
     dev_free(sys, sys->ell.tmp_where);
@@ -695,6 +702,7 @@ int ell_build(bdg_system *sys) {
     e.dict_usable = false;
     e.diag_usable = false;
     e.pair_usable = false;
+    e.cube_usable = false;
     e.n_unique = 0;
     e.n_sites = n;
     if (n > 0) {
@@ -722,6 +730,7 @@ int ell_build(bdg_system *sys) {
             e.usable = true;
             BDG_TRY(dict_build(sys));
             BDG_TRY(pair_probe(sys));
+            BDG_TRY(cube_probe(sys));
         }
     }
     e.valid = true;
@@ -765,6 +774,9 @@ int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok) {
     a.dcode = e.pair_usable ? e.dcode.as<int32_t>() : nullptr;
     a.Lx = sys->cubic[0];
     a.M = e.pair_M;
+    a.dcode3 = e.cube_usable ? e.dcode3.as<int32_t>() : nullptr;
+    a.Ly = sys->cubic[1];
+    a.Lz = sys->cubic[2];
     a.status = e.counters.as<int>();
     patch_blocks<<<(unsigned)ceil_div(n * 32, 256), 256, 0, sys->stream>>>(n, klist, a);
     BDG_CUDA(cudaGetLastError());

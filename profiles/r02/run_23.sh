@@ -1,0 +1,9 @@
+# round 2, call 23: first run of the three-dimensional even-vector kernel (cheb_cube.cu): its tests, C4 timing per patch shape
+set -x
+mkdir -p gpurun_out/r02
+( time timeout 900 python -m pytest tests/test_gpu_cube.py -x -q 2>&1 | tail -15 ) 2>&1 | tee gpurun_out/r02/23_pytest_cube.log
+for shape in 0 1 2; do
+  echo "== BDG_CUBE_SHAPE=$shape"
+  BDG_CUBE_SHAPE=$shape QP_STEPS=400 timeout 300 python profiles/quickperf2.py C4:8:t2 C4:64:t2 2>&1 | cut -c1-230
+done 2>&1 | tee gpurun_out/r02/23_quickperf_c4_cube.log
+QP_STEPS=400 timeout 300 python profiles/quickperf2.py C4:8:dict_diag C4:64:dict_diag 2>&1 | cut -c1-230 | tee -a gpurun_out/r02/23_quickperf_c4_cube.log

@@ -58,7 +58,7 @@ def test_full_size_assembly_equals_the_oracle(full, key):
 
 @pytest.mark.parametrize("key,kernels", [
     ("C5", ["auto", "pair", "dict_diag", "dict", "ell", "dmma"]),
-    ("C4", ["auto", "dict", "ell", "dmma"]),
+    ("C4", ["auto", "dict_diag", "dict", "ell", "dmma"]),   # auto = the even-vector recursion of cheb_cube.cu
     ("C5_disordered", ["auto", "pair", "dict_diag", "ell"]),
     ("C5_random", ["auto", "dmma"]),
     ("C5_periodic", ["auto", "pair", "dict_diag", "ell"]),   # wrap-around halos of 72 patches x 4 segments at full size
@@ -74,6 +74,8 @@ def test_full_size_moments_equal_the_oracle(full, key, kernels):
         assert np.array_equal(got[0], want[0])  # <x|x> = 4N exactly
     if key == "C5":
         assert {"t2", "pair", "dict_diag", "dict", "ell", "dmma"} <= seen
+    if key == "C4":
+        assert {"t2", "dict_diag", "dict", "ell", "dmma"} <= seen
     if key == "C5_random":
         assert "ell" in seen  # nothing repeats: the matrix is streamed
     if key == "C5_periodic":

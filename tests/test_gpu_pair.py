@@ -236,7 +236,8 @@ def test_one_call_c_entry_point(gpu_api):
     from bodge_b200 import _native
 
     lib = _native.load()
-    for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
+    for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "t2"),
+                                (cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict")):
         H = system.matrix("bsr")
         scale = system.spectral_bound()
         x0 = orc.rademacher(77, H.shape[0], np.arange(8) + 2)
@@ -378,14 +379,13 @@ def test_t2_observables_and_auto_moments(gpu_api):
     F = system.free_energy(0.1, cuda=True, vectors=16, moments=512)
     assert system._sys.cheb_format()["kernel"] == "t2"
     assert abs(F - system.free_energy(0.1, cuda=True, vectors=16, moments=512, kernel="dict_diag")) <= 1e-10 * abs(F)
-    # where the pair kernel is not the stepping default, auto_moments is plain auto
-    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
+    # where no two-applications-per-pass kernel applies, auto_moments is plain auto (complex hopping blocks; three-dimensional
+    # lattices have their own even-vector kernel: tests/test_gpu_cube.py)
+    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "t2")):
         other.chebyshev_moments(16, vectors=8, seed=1)
         assert other._sys.cheb_format()["kernel"] == want
     system.chebyshev_moments(16, vectors=4, seed=1)
     assert system._sys.cheb_format()["kernel"] == "t2"         # 1200 sites: four columns are padded to a panel
-    with pytest.raises(ValueError):
-        cases.swave_3d(gpu_api, (6, 5, 4))._sys.cheb_begin(n_random=8, seed=1, scale=10.0, kernel="t2")
 
 
 def test_pair_full_size_junction():
