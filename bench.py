@@ -598,6 +598,11 @@ def run_ours(args):
                 sysx = B.build(key)
                 t = B.timed(sysx, kc, args.kernel, K, W, min_s=0.3)
                 others[key] = B.summary(t, key, kc, jobs=jobs)
+                if key == "C4" and others[key]["kernel"] == "t2":
+                    # three-dimensional lattice: the even-vector kernel (csrc/cheb_cube.cu) moves half the bytes in about the
+                    # time of the single-step kernel -- both, so that steps/s and the roofline fraction can be read side by side
+                    t1 = B.timed(sysx, kc, "dict_diag", K, W, min_s=0.3)
+                    others["C4_single_step"] = B.summary(t1, key, kc, jobs=jobs)
                 del sysx
             except (RuntimeError, ValueError, MemoryError) as err:
                 others[key] = {"error": str(err)[:200]}

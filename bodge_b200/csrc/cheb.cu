@@ -570,7 +570,11 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
         const bool prefer = pair_ok && sys->ell.diag_usable && auto_pair_enabled();
         // Callers that only read moments / observables get the even-vector recursion (three vector passes per
         // two steps); callers that step and look at T_n, T_{n-1} the pair kernel (four).
-        t2 = kernel == BDG_KERNEL_T2 || (kernel == BDG_KERNEL_AUTO_MOMENTS && (prefer || (cube_ok && auto_cube_enabled())));
+        // ... preferred where its items fill the machine without cutting x into segments (one CTA per SM marches an 8 x 8 patch:
+        // C4 = 64 patches x 2 panels); on smaller lattices the single-step kernel's finer grid wins.
+        const int64_t cube_items = ceil_div(sys->cubic[1], 8) * ceil_div(sys->cubic[2], 8) * ceil_div(n_cols, 4);
+        const bool prefer_cube = cube_ok && auto_cube_enabled() && 4 * cube_items >= 3 * (int64_t)sys->sm_count;
+        t2 = kernel == BDG_KERNEL_T2 || (kernel == BDG_KERNEL_AUTO_MOMENTS && (prefer || prefer_cube));
         cube = t2 && !pair_ok && cube_ok;
         pair = kernel == BDG_KERNEL_PAIR || (kernel == BDG_KERNEL_AUTO && prefer);
         if (kernel == BDG_KERNEL_PAIR || kernel == BDG_KERNEL_T2 || kernel == BDG_KERNEL_AUTO_MOMENTS) kernel = BDG_KERNEL_AUTO;

@@ -63,8 +63,17 @@ struct Held {
     bool two = false;           // the two sites have different on-site blocks
 };
 
+// The reload path is taken a few times per item, but its loads would share a scoreboard with the prefetches issued at the
+// top of every iteration (ptxas has six): the first MMA after the branch then waits for those prefetches -- a full HBM
+// latency per iteration (ncu: 17 % of all stall samples on that one instruction, profiles/r02/24_cube_c4k8_v1_hot_instructions.txt).
+// An integer operation on the loaded value INSIDE the branch waits there instead, and what leaves the branch is the result
+// of a fixed-latency instruction.
+__device__ __forceinline__ double settle(double v, int n_panels /* > 0: the XOR mask is a zero the compiler cannot see through */) {
+    return __longlong_as_double(__double_as_longlong(v) ^ (long long)(n_panels >> 30));
+}
+
 __device__ __forceinline__ void hold_cube(int jv, Held &H, const double *__restrict__ table, const double *__restrict__ dtab,
-                                          int lane) {
+                                          int lane, int n_panels) {
     const bool code_lane = lane < 16 && (lane & 7) < 7;
     const unsigned changed = __ballot_sync(kFull, code_lane && jv != H.jheld && jv != -2);
     if (changed) {
@@ -72,8 +81,8 @@ __device__ __forceinline__ void hold_cube(int jv, Held &H, const double *__restr
         const bool upper = lane >= 16;
         if (changed & 0x0101u) {
             const int c0 = __shfl_sync(kFull, H.jheld, 0), c1 = __shfl_sync(kFull, H.jheld, 8);
-            H.b0 = c0 >= 0 ? __ldg(table + (size_t)c0 * 32 + lane) : 0.0;
-            H.b1 = c1 >= 0 ? __ldg(table + (size_t)c1 * 32 + lane) : 0.0;
+            H.b0 = settle(c0 >= 0 ? __ldg(table + (size_t)c0 * 32 + lane) : 0.0, n_panels);
+            H.b1 = settle(c1 >= 0 ? __ldg(table + (size_t)c1 * 32 + lane) : 0.0, n_panels);
             H.two = c0 != c1;
         }
 #pragma unroll
@@ -81,7 +90,7 @@ __device__ __forceinline__ void hold_cube(int jv, Held &H, const double *__restr
             if (changed & (0x0101u << u)) {
                 const int c0 = __shfl_sync(kFull, H.jheld, u), c1 = __shfl_sync(kFull, H.jheld, 8 + u);
                 const int c = upper ? c1 : c0;
-                H.h[u] = c >= 0 ? __ldg(dtab + (size_t)c * 4 + (lane & 3)) : 0.0;
+                H.h[u] = settle(c >= 0 ? __ldg(dtab + (size_t)c * 4 + (lane & 3)) : 0.0, n_panels);
             }
         }
     }
@@ -295,7 +304,7 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                 for (int r = 0; r < RA; ++r) {
                     if (warp + NW * r < NA) {
-                        hold_cube(jA[r], H, table, dtab, lane);
+                        hold_cube(jA[r], H, table, dtab, lane, n_panels);
                         const uint32_t a = eC + aE[r];
                         const double2 own = lds_rec(a), xm = lds_rec(eM + aE[r]), ym = lds_rec(a - EZ * R), zm = lds_rec(a - R);
                         const double2 zp = lds_rec(a + R), yp = lds_rec(a + EZ * R);
@@ -328,7 +337,7 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     if (warp + NW * r < NB) {
-                        hold_cube(jB[r], H, table, dtab, lane);
+                        hold_cube(jB[r], H, table, dtab, lane, n_panels);
                         const uint32_t a = uC + bU[r];
                         const double2 own = lds_rec(a), xm = lds_rec(uM + bU[r]), ym = lds_rec(a - UZ * R), zm = lds_rec(a - R);
                         const double2 zp = lds_rec(a + R), yp = lds_rec(a + UZ * R), xp = lds_rec(uW + bU[r]);

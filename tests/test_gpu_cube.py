@@ -118,19 +118,24 @@ def test_cube_probe_columns_observables_and_auto(gpu_api):
     scale = system.spectral_bound()
     sites = [(0, 0, 0), (8, 9, 10), (4, 7, 8), (4, 8, 7), (3, 0, 10), (5, 9, 0)]
     rows = [4 * system.lattice.index(s) + a for s in sites for a in (0, 3)]
-    got = system.chebyshev_moments(64, rows=rows, scale=scale)
+    got = system.chebyshev_moments(64, rows=rows, scale=scale, kernel="t2")
     assert system._sys.cheb_format()["kernel"] == "t2" and system._sys.cheb_info()["panel_width"] == 4
     x0 = np.zeros((H.shape[0], len(rows)), dtype=np.complex128)
     x0[rows, np.arange(len(rows))] = 1.0
     assert rel_err(got, orc.cheb_moments(H, x0, 64, scale)) <= TOL
     E = np.linspace(-0.3, 0.3, 9)
-    assert rel_err(system.ldos_map(sites[:2], E), system.ldos_map(sites[:2], E, kernel="dict_diag")) <= 1e-10
+    assert rel_err(system.ldos_map(sites[:2], E, kernel="t2"), system.ldos_map(sites[:2], E, kernel="dict_diag")) <= 1e-10
     small = cases.swave_3d(gpu_api, (5, 4, 4))
-    F = small.free_energy(0.1, cuda=True)                      # exact trace: 320 columns = 80 panels of four
+    F = small.free_energy(0.1, cuda=True, kernel="t2")         # exact trace: 320 columns = 80 panels of four
     assert small._sys.cheb_format()["kernel"] == "t2"
     assert abs(F - small.free_energy(0.1)) <= 1e-10 * abs(F)   # ... against the reference's dense algorithm
-    # the stepping API keeps T_n and T_{n-1}: single-step kernel; BDG_AUTO_CUBE=0 turns the preference off
-    small._sys.cheb_begin(n_random=8, seed=1, scale=10.0, kernel="auto")
+    # The observables' default picks it where its items fill the machine (>= 3/4 of the SMs get an 8 x 8 patch of a 4-column
+    # panel without cutting x): 2000 columns on this lattice do, 8 do not.  The stepping API keeps T_n and T_{n-1}: single step.
+    small.chebyshev_moments(16, vectors=2000, seed=1)
+    assert small._sys.cheb_format()["kernel"] == "t2"
+    small.chebyshev_moments(16, vectors=8, seed=1)
+    assert small._sys.cheb_format()["kernel"] == "dict_diag"
+    small._sys.cheb_begin(n_random=2000, seed=1, scale=10.0, kernel="auto")
     assert small._sys.cheb_format()["kernel"] == "dict_diag"
     small._sys.cheb_end()
 
@@ -149,7 +154,7 @@ def test_cube_declines_what_it_cannot_do(gpu_api, monkeypatch):
     with pytest.raises(ValueError):
         three_d._sys.cheb_begin(n_random=8, seed=1, scale=scale, kernel="t2")
     Hm = three_d.matrix("bsr")
-    got = three_d.chebyshev_moments(16, vectors=8, seed=2)              # auto: back on the single-step kernel
+    got = three_d.chebyshev_moments(16, vectors=2000, seed=2)[:, :8]    # auto: the single-step kernel, however many columns
     assert three_d._sys.cheb_format()["kernel"] == "dict_diag"
     assert rel_err(got, orc.cheb_moments(Hm, orc.rademacher(2, Hm.shape[0], np.arange(8)), 16, three_d.spectral_bound())) <= TOL
     complex_hop = cases.swave_3d(gpu_api, (4, 4, 4))
@@ -158,11 +163,13 @@ def test_cube_declines_what_it_cannot_do(gpu_api, monkeypatch):
         H[(1, 1, 2), (1, 1, 1)] = -1.0 * gpu_api.σ0 - 0.2j * gpu_api.σ1
     with pytest.raises(ValueError):
         complex_hop._sys.cheb_begin(n_random=8, seed=1, scale=scale, kernel="t2")
-    monkeypatch.setenv("BDG_AUTO_CUBE", "0")
     plain = cases.swave_3d(gpu_api, (6, 5, 4))
-    plain.chebyshev_moments(16, vectors=8, seed=1)
+    plain.chebyshev_moments(16, vectors=2000, seed=1)                  # 500 panels: enough items
+    assert plain._sys.cheb_format()["kernel"] == "t2"
+    monkeypatch.setenv("BDG_AUTO_CUBE", "0")                            # the preference can be switched off ...
+    plain.chebyshev_moments(16, vectors=2000, seed=1)
     assert plain._sys.cheb_format()["kernel"] == "dict_diag"
-    plain.chebyshev_moments(16, vectors=8, seed=1, kernel="t2")        # asking for it by name still works
+    plain.chebyshev_moments(16, vectors=8, seed=1, kernel="t2")        # ... asking for the kernel by name still works
     assert plain._sys.cheb_format()["kernel"] == "t2"
 
 

@@ -236,7 +236,7 @@ def test_one_call_c_entry_point(gpu_api):
     from bodge_b200 import _native
 
     lib = _native.load()
-    for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "t2"),
+    for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag"),
                                 (cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict")):
         H = system.matrix("bsr")
         scale = system.spectral_bound()
@@ -379,9 +379,9 @@ def test_t2_observables_and_auto_moments(gpu_api):
     F = system.free_energy(0.1, cuda=True, vectors=16, moments=512)
     assert system._sys.cheb_format()["kernel"] == "t2"
     assert abs(F - system.free_energy(0.1, cuda=True, vectors=16, moments=512, kernel="dict_diag")) <= 1e-10 * abs(F)
-    # where no two-applications-per-pass kernel applies, auto_moments is plain auto (complex hopping blocks; three-dimensional
-    # lattices have their own even-vector kernel: tests/test_gpu_cube.py)
-    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "t2")):
+    # where no two-applications-per-pass kernel applies or pays, auto_moments is plain auto (complex hopping blocks; small
+    # three-dimensional lattices -- large ones have their own even-vector kernel: tests/test_gpu_cube.py)
+    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
         other.chebyshev_moments(16, vectors=8, seed=1)
         assert other._sys.cheb_format()["kernel"] == want
     system.chebyshev_moments(16, vectors=4, seed=1)
