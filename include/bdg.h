@@ -134,7 +134,11 @@ enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
  *        (<E_j,E_j>, <H~E_j,E_j>, <E_{j+1},E_j>, <E_{j+1},H~E_j>) give the same four moments through
  *        T_m T_n = (T_{m+n} + T_|m-n|)/2 (odd ones by a two-term recurrence).  Steps advance in twos (an odd
  *        bdg_cheb_steps request is rounded up), bdg_cheb_begin already performs the first (T_2), and
- *        bdg_cheb_vectors(which = 1) is not available.  Same requirements as PAIR;
+ *        bdg_cheb_vectors(which = 1) is not available.  Same requirements as PAIR (open or periodic stencil) -- or a
+ *        THREE-DIMENSIONAL lattice (Ly, Lz >= 2) with an open nearest-neighbour stencil, real-diagonal hopping blocks,
+ *        <= 64 distinct blocks and >= 3 columns: there it runs on 4-column panels (bdg_cheb_info: panel_width = 4) with a
+ *        kernel of its own (csrc/cheb_cube.cu), which AUTO_MOMENTS prefers when its work items fill the GPU (e.g. 64^3 sites
+ *        with >= 8 columns); BDG_AUTO_CUBE=0 in the environment switches that preference off;
  * PAIR = two recursion steps per launch on the DICT / DICT_DIAG format: T_{n+1} is consumed out of shared
  *        memory instead of coming back from HBM, so two steps move four vector passes instead of six.  Needs
  *        >= 5 columns and a lattice with one-dimensional x-planes (Lz = 1 or Ly = 1) whose stored blocks form
