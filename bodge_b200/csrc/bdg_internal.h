@@ -144,6 +144,7 @@ struct EllDev {
     //   code  int32  [n_sites][width]          table double [n_unique][4][2][4]
     bool dict_usable = false;
     bool diag_usable = false;  // every block outside slot 0 is real and diagonal: dtab[n_unique][4] holds the diagonals
+    bool self_diag_usable = false;  // every block IN slot 0 (on-site) is real and diagonal (cheb_step_ell<..., SD>)
     int64_t n_unique = 0;
     DevBuf code, table, dtab;
     // Two-steps-per-pass kernel (cheb_pair.cu): dictionary format + nearest-neighbour stencil on a

@@ -567,7 +567,11 @@ extern "C" int bdg_cheb_begin(bdg_t *sys, int kind, int32_t n_cols, const int64_
                     "the even-vector recursion needs a block dictionary on a lattice with a nearest-neighbour stencil: one-dimensional "
                     "x-planes and >= 5 columns, or a three-dimensional open lattice with real-diagonal hopping blocks, <= 64 "
                     "distinct blocks and >= 3 columns (any number of columns on lattices of <= 65536 sites)");
-        const bool prefer = pair_ok && sys->ell.diag_usable && auto_pair_enabled();
+        // The two-step kernels pay on every dictionary matrix they take (round 2, profiles/r02/41_* .. 43_*): rows of real-
+        // diagonal hopping blocks (DFMA), general hopping blocks next to real-diagonal on-site blocks (SD: d-wave / Rashba
+        // models, +12..44 % over the single-step kernel) and rows of ten MMAs (+22..42 % at 8 columns, +24..32 % at >= 64
+        // columns on 10^6 sites, level at C3 with 64..512 columns).
+        const bool prefer = pair_ok && auto_pair_enabled();
         // Callers that only read moments / observables get the even-vector recursion (three vector passes per
         // two steps); callers that step and look at T_n, T_{n-1} the pair kernel (four).
         // ... preferred where its items fill the machine without cutting x into segments (one CTA per SM marches an 8 x 8 patch:
@@ -816,7 +820,8 @@ extern "C" int bdg_cheb_format(bdg_t *sys, int32_t *kernel, int64_t *matrix_byte
         if (st.cube)  // eight 4-byte codes per site, read once per panel and launch (= two steps)
             *matrix_bytes_per_step = e.n_sites * 32 * st.n_panels / 2 + e.n_unique * 256;
         else if (st.pair || st.t2)  // one pass over the codes (and, site-dependent on-site blocks: over those) serves two steps
-            *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + (pair_streams_onsite(sys) ? std::min(e.n_unique, e.n_sites) * 256 / 2 : e.n_unique * 256);
+            *matrix_bytes_per_step = e.n_sites * 5 * 4 / 2 + (pair_streams_onsite(sys) ? std::min(e.n_unique, e.n_sites) * (e.self_diag_usable && !e.diag_usable ? 32 : 256) / 2
+                                                                                        : e.n_unique * 256);
         else if (st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG)
             *matrix_bytes_per_step = e.n_sites * e.width * 8 + e.n_unique * 256;
         else if (st.kernel == BDG_KERNEL_ELL)

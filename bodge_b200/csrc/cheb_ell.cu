@@ -72,7 +72,13 @@ __device__ __forceinline__ void ld_table_if(double &v, const double *p, unsigned
 // occupy the FP64 pipe 16 cycles each) and the held "fragment" is the lane's diagonal entry from
 // `dtab[code][4]`.  Once the dictionary has taken the matrix out of the HBM stream the FP64 pipe is
 // the next limiter (ncu: math-pipe-throttle stalls), which this removes for the common models.
-template <int PW, int CH, int NP, int PB, bool DICT, bool DIAG>
+//
+// SD (with DICT, without DIAG) = every block in slot 0 -- the on-site block -- is real and diagonal (a chemical potential
+// and a Zeeman sigma_3 term without on-site pairing: d-wave / p-wave models, Rashba wires) while the hopping blocks are
+// general: the on-site product is two multiplications instead of two MMAs (a tenth of the row's FP64-pipe time at five
+// blocks per row; the complex-hopping models are the ones the FP64 pipe bounds).  The MMA accumulators START from those
+// products, which is what the MMA of a real-diagonal block leaves in them: same sums, same order as DICT.
+template <int PW, int CH, int NP, int PB, bool DICT, bool DIAG, bool SD = false>
 __global__ void __launch_bounds__(kThreads, 4)
 cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode, const double *__restrict__ cdata,
               const double *__restrict__ dtab, const double2 *__restrict__ x_cur, double2 *__restrict__ x_io, int n_sites, int n_panels, double alpha,
@@ -166,7 +172,7 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const int code = __shfl_sync(kFull, jv, 8 + u);
-                    const double *entry = (DIAG && u > 0) ? dtab + (size_t)code * 4 + (lane & 3) : cdata + (size_t)code * 32 + lane;
+                    const double *entry = ((DIAG && u > 0) || (SD && u == 0)) ? dtab + (size_t)code * 4 + (lane & 3) : cdata + (size_t)code * 32 + lane;
                     ld_table_if(keep[u], entry, changed >> u & 1u);
                 }
             }
@@ -206,8 +212,9 @@ cheb_step_ell(const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccod
 #pragma unroll
             for (int pp = 0; pp < PB; ++pp) {
                 double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0;
+                if (SD) a10 = bop[0] * xv[pp][0].x, a20 = bop[0] * xv[pp][0].y;
 #pragma unroll
-                for (int u = 0; u < (DIAG ? 1 : CH); ++u) {
+                for (int u = SD ? 1 : 0; u < (DIAG ? 1 : CH); ++u) {
                     dmma_8x8x4(a10, a11, xv[pp][u].x, bop[u]);
                     dmma_8x8x4(a20, a21, xv[pp][u].y, bop[u]);
                 }
@@ -379,20 +386,20 @@ dict_diag_table(int n_unique, const double *__restrict__ table, double *__restri
     if (lane == 0) isdiag[w] = other == 0u;
 }
 
-// *bad = 1 if any slot other than slot 0 holds a block that is not real-diagonal.
+// bad[0] = 1 if any slot other than slot 0 holds a block that is not real-diagonal, bad[1] = 1 if any slot 0 does.
 __global__ void __launch_bounds__(256)
 dict_offsite_diag(int64_t n_slots, int width, const int32_t *__restrict__ ccode, const int *__restrict__ isdiag,
                   int *__restrict__ bad) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_slots || t % width == 0) return;
-    if (!isdiag[ccode[t]]) *bad = 1;
+    if (t >= n_slots) return;
+    if (!isdiag[ccode[t]]) bad[t % width == 0 ? 1 : 0] = 1;
 }
 
 // ---- incremental update after a scatter (re-enter `with`, change a few terms, ask again) -----------
 // One warp per touched skeleton block: copy it into its place in `packed`, into its fixed-width slot (fragment
 // order), look it up in -- or add it to -- the dictionary and rewrite the slot's code (and direction code).
 // status: [0] distinct blocks so far, [1] zero pattern changed, [2] table full, [3] hash collision, [4] an
-// off-site block that is not real-diagonal (the DIAG kernels no longer apply).
+// off-site block that is not real-diagonal (the DIAG kernels no longer apply), [5] an on-site block that is not (SD).
 struct PatchArgs {
     const int32_t *s_indices, *s_brow;
     const double *s_data;
@@ -407,7 +414,7 @@ struct PatchArgs {
     int32_t *posid;
     unsigned cap_mask;
     double *table, *dtab;
-    int table_cap, diag_required;
+    int table_cap, diag_required, self_diag_required;
     int32_t *dcode;
     int Lx, M;
     int32_t *dcode3;
@@ -504,6 +511,7 @@ patch_blocks(int64_t n, const int32_t *__restrict__ klist, const PatchArgs a) {
     }
     if (lane == 0) {
         if (u > 0 && a.diag_required && !isdiag) a.status[4] = 1;
+        if (u == 0 && a.self_diag_required && !isdiag) a.status[5] = 1;  // the SD variants no longer apply: the plain ones take over
         a.ccode[slot] = id;
         if (a.dcode) {
             const int dir = u == 0 ? 0 : torus_direction(row, col, a.Lx, a.M);
@@ -519,35 +527,40 @@ patch_blocks(int64_t n, const int32_t *__restrict__ klist, const PatchArgs a) {
 using EllKernel = void (*)(const int32_t *, const int32_t *, const double *, const double *, const double2 *, double2 *,
                            int, int, double, double, int, int, double *, unsigned *, double *, const RowWalk);
 
-template <int PW, int NP, int PB, bool DICT, bool DIAG> EllKernel pick_ch(int width) {
+template <int PW, int NP, int PB, bool DICT, bool DIAG, bool SD> EllKernel pick_ch(int width) {
     switch (width) {
-        case 3: return cheb_step_ell<PW, 3, NP, PB, DICT, DIAG>;
-        case 4: return cheb_step_ell<PW, 4, NP, PB, DICT, DIAG>;
-        case 5: return cheb_step_ell<PW, 5, NP, PB, DICT, DIAG>;
-        case 6: return cheb_step_ell<PW, 6, NP, PB, DICT, DIAG>;
-        case 7: return cheb_step_ell<PW, 7, NP, PB, DICT, DIAG>;
-        default: return cheb_step_ell<PW, 8, NP, PB, DICT, DIAG>;
+        case 3: return cheb_step_ell<PW, 3, NP, PB, DICT, DIAG, SD>;
+        case 4: return cheb_step_ell<PW, 4, NP, PB, DICT, DIAG, SD>;
+        case 5: return cheb_step_ell<PW, 5, NP, PB, DICT, DIAG, SD>;
+        case 6: return cheb_step_ell<PW, 6, NP, PB, DICT, DIAG, SD>;
+        case 7: return cheb_step_ell<PW, 7, NP, PB, DICT, DIAG, SD>;
+        default: return cheb_step_ell<PW, 8, NP, PB, DICT, DIAG, SD>;
     }
 }
 
-template <bool DICT, bool DIAG> EllKernel pick_shape(int pw, int np, int pb, int width) {
+template <bool DICT, bool DIAG, bool SD = false> EllKernel pick_shape(int pw, int np, int pb, int width) {
     switch (pw) {
-        case 1: return pick_ch<1, 1, 1, DICT, DIAG>(width);
-        case 2: return pick_ch<2, 1, 1, DICT, DIAG>(width);
-        case 4: return pick_ch<4, 1, 1, DICT, DIAG>(width);
+        case 1: return pick_ch<1, 1, 1, DICT, DIAG, SD>(width);
+        case 2: return pick_ch<2, 1, 1, DICT, DIAG, SD>(width);
+        case 4: return pick_ch<4, 1, 1, DICT, DIAG, SD>(width);
         default:
-            if (np >= 8) return pick_ch<8, 8, 1, DICT, DIAG>(width);
-            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2, DICT, DIAG>(width) : pick_ch<8, 4, 1, DICT, DIAG>(width);
-            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2, DICT, DIAG>(width) : pick_ch<8, 2, 1, DICT, DIAG>(width);
-            return pick_ch<8, 1, 1, DICT, DIAG>(width);
+            if (np >= 8) return pick_ch<8, 8, 1, DICT, DIAG, SD>(width);
+            if (np >= 4) return pb >= 2 ? pick_ch<8, 4, 2, DICT, DIAG, SD>(width) : pick_ch<8, 4, 1, DICT, DIAG, SD>(width);
+            if (np >= 2) return pb >= 2 ? pick_ch<8, 2, 2, DICT, DIAG, SD>(width) : pick_ch<8, 2, 1, DICT, DIAG, SD>(width);
+            return pick_ch<8, 1, 1, DICT, DIAG, SD>(width);
     }
 }
 
-// fmt: BDG_KERNEL_ELL, BDG_KERNEL_DICT or BDG_KERNEL_DICT_DIAG
-EllKernel pick_ell(int fmt, int pw, int np, int pb, int width) {
+// fmt: BDG_KERNEL_ELL, BDG_KERNEL_DICT or BDG_KERNEL_DICT_DIAG; self_diag: DICT with real-diagonal on-site blocks (SD)
+EllKernel pick_ell(int fmt, int pw, int np, int pb, int width, bool self_diag) {
     if (fmt == BDG_KERNEL_DICT_DIAG) return pick_shape<true, true>(pw, np, pb, width);
-    if (fmt == BDG_KERNEL_DICT) return pick_shape<true, false>(pw, np, pb, width);
+    if (fmt == BDG_KERNEL_DICT) return self_diag ? pick_shape<true, false, true>(pw, np, pb, width) : pick_shape<true, false>(pw, np, pb, width);
     return pick_shape<false, false>(pw, np, pb, width);
+}
+
+bool ell_self_diag(const EllDev &e) {
+    const char *v = getenv("BDG_ELL_SD");
+    return e.self_diag_usable && (v && *v ? atoi(v) != 0 : true);
 }
 
 int env_int(const char *name, int fallback) {
@@ -657,18 +670,20 @@ int dict_build(bdg_system *sys) {
     e.dict_usable = host[3] == 0 && host[2] == n_unique;  // no hash collision, table fully written
     // Real-diagonal off-site blocks (DIAG kernels)?
     e.diag_usable = false;
+    e.self_diag_usable = false;
     if (e.dict_usable) {
         BDG_TRY(dev_alloc(sys, e.dtab, (size_t)e.table_cap * 4 * sizeof(double)));
         BDG_TRY(dev_alloc(sys, e.tmp_rep, (size_t)std::max<int64_t>(cap, n_unique) * sizeof(int)));  // reuse as isdiag[]
-        BDG_CUDA(cudaMemsetAsync(scal, 0, sizeof(int), sys->stream));
+        BDG_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(int), sys->stream));
         dict_diag_table<<<(unsigned)ceil_div((int64_t)n_unique * 32, 256), 256, 0, sys->stream>>>(
             n_unique, e.table.as<double>(), e.dtab.as<double>(), e.tmp_rep.as<int>());
         dict_offsite_diag<<<(unsigned)ceil_div(n_slots, 256), 256, 0, sys->stream>>>(
             n_slots, e.width, e.code.as<int32_t>(), e.tmp_rep.as<int>(), scal);
         BDG_CUDA(cudaGetLastError());
-        BDG_CUDA(cudaMemcpyAsync(host, scal, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+        BDG_CUDA(cudaMemcpyAsync(host, scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
         BDG_CUDA(cudaStreamSynchronize(sys->stream));
         e.diag_usable = host[0] == 0;
+        e.self_diag_usable = host[1] == 0;
     }
     return BDG_OK;
 }
@@ -701,6 +716,7 @@ int ell_build(bdg_system *sys) {
     e.usable = false;
     e.dict_usable = false;
     e.diag_usable = false;
+    e.self_diag_usable = false;
     e.pair_usable = false;
     e.cube_usable = false;
     e.n_unique = 0;
@@ -750,7 +766,7 @@ int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok) {
     const bool dict = e.usable && e.dict_usable;
     if (e.usable && !dict && e.n_unique > 0) return BDG_OK;  // a dictionary was attempted and given up: rebuild decides again
     BDG_TRY(dev_alloc(sys, e.counters, 8 * sizeof(int)));
-    int host[5] = {(int)e.n_unique, 0, 0, 0, 0};
+    int host[6] = {(int)e.n_unique, 0, 0, 0, 0, 0};
     BDG_CUDA(cudaMemcpyAsync(e.counters.ptr, host, sizeof(host), cudaMemcpyHostToDevice, sys->stream));
     PatchArgs a{};
     a.s_indices = sys->skel.indices.as<int32_t>();
@@ -771,6 +787,7 @@ int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok) {
     a.dtab = e.dtab.as<double>();
     a.table_cap = (int)e.table_cap;
     a.diag_required = e.diag_usable ? 1 : 0;
+    a.self_diag_required = e.self_diag_usable && !e.diag_usable ? 1 : 0;  // (only the SD kernel relies on it)
     a.dcode = e.pair_usable ? e.dcode.as<int32_t>() : nullptr;
     a.Lx = sys->cubic[0];
     a.M = e.pair_M;
@@ -784,6 +801,7 @@ int ell_patch(bdg_system *sys, int64_t n, const int32_t *klist, bool *ok) {
     BDG_CUDA(cudaStreamSynchronize(sys->stream));
     if (host[1] || host[2] || host[3] || host[4]) return BDG_OK;  // pattern / capacity / collision / DIAG precondition: rebuild
     e.n_unique = host[0];
+    if (host[5]) e.self_diag_usable = false;  // an on-site block with off-diagonal entries: same format, MMA on-site product
     *ok = true;
     return BDG_OK;
 }
@@ -809,7 +827,7 @@ int ell_configure(bdg_system *sys) {
     st.n_groups = (int)ceil_div(st.n_panels, st.panels_per_group);
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width), kThreads,
+        &per_sm, pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width, ell_self_diag(e)), kThreads,
         (size_t)env_int("BDG_ELL_PAD", 0)));
     per_sm = std::max(per_sm, 1);
     const int64_t slots = std::max<int64_t>(1, (int64_t)sys->sm_count * per_sm / st.n_groups);
@@ -822,7 +840,7 @@ int ell_launch_step(bdg_system *sys, bool first, const void *x_cur, void *x_io, 
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
     const bool dict = st.kernel == BDG_KERNEL_DICT || st.kernel == BDG_KERNEL_DICT_DIAG;
-    EllKernel k = pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width);
+    EllKernel k = pick_ell(st.kernel, st.panel_width, st.panels_per_group, st.panel_batch, e.width, ell_self_diag(e));
     // Stream the matrix through L2 (evict-first) only when nothing will read it again soon: one
     // group per pass and a matrix that cannot stay resident in the 126 MB L2 anyway.
     const size_t matrix_bytes = (size_t)e.n_sites * e.width * 260;

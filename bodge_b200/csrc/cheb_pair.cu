@@ -59,7 +59,7 @@ constexpr int kDirs = 5;  // direction-ordered row: self, x-1, y-1, y+1, x+1 (= 
 // plane and reloaded only when a code differs from the held one.  Lane s * 5 + u carries the code of
 // row s, direction u; code < 0 = no block.  SELF: the on-site fragments (u = 0) are not held -- they are
 // fetched per row, one plane ahead (self_fragments) -- so their codes do not take part in the test.
-template <bool DIAG, bool SELF, int S>
+template <bool DIAG, bool SELF, int S, bool SD = false>
 __device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep)[S][kDirs], const double *__restrict__ table,
                                                const double *__restrict__ dtab, int lane, bool self_lane) {
     const unsigned changed = __ballot_sync(kFull, jv != jheld && !(SELF && self_lane));
@@ -72,7 +72,7 @@ __device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep
                 const int code = __shfl_sync(kFull, jv, s * kDirs + u);
                 const unsigned take = changed >> (s * kDirs + u) & 1u;
                 const size_t c = (size_t)max(code, 0);
-                const double *entry = (DIAG && u > 0) ? dtab + c * 4 + (lane & 3) : table + c * 32 + lane;
+                const double *entry = ((DIAG && u > 0) || (SD && u == 0)) ? dtab + c * 4 + (lane & 3) : table + c * 32 + lane;
                 ld_table_pred(keep[s][u], entry, take && code >= 0);
                 if (take && code < 0) keep[s][u] = 0.0;
             }
@@ -84,22 +84,29 @@ __device__ __forceinline__ void hold_fragments(int jv, int &jheld, double (&keep
 // (-1: no diagonal block -> 0).  Issued a plane ahead of its use; with every on-site block distinct (disorder,
 // self-consistent gap) this is the 256-byte-per-site stream the matrix cannot do without, with a phase winding
 // or a layered structure it hits in L1 / L2.
-template <int S>
-__device__ __forceinline__ void self_fragments(int jv, double (&f)[S], const double *__restrict__ table, int lane) {
+template <int S, bool SD = false>
+__device__ __forceinline__ void self_fragments(int jv, double (&f)[S], const double *__restrict__ table, const double *__restrict__ dtab,
+                                               int lane) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const int code = __shfl_sync(kFull, jv, s * kDirs);
         f[s] = 0.0;
-        ld_table_pred(f[s], table + (size_t)max(code, 0) * 32 + lane, code >= 0);
+        ld_table_pred(f[s], SD ? dtab + (size_t)max(code, 0) * 4 + (lane & 3) : table + (size_t)max(code, 0) * 32 + lane, code >= 0);
     }
 }
 
 // y = sum_u B_u x_u for this lane's element; order and operations of cheb_step_ell (directions: self, x-1, y-1,
 // y+1, x+1 = ascending block column on an open lattice), in stages so that sub-step [B] can start on the records its
 // own warp wrote while the rest of the CTA is still arriving at the barrier: begin (self), add x 4, end.
-template <bool DIAG> struct RowSum {
+// SD (without DIAG): the on-site block is real and diagonal (cheb_ell.cu: SD) -- its product is two multiplications, and
+// the accumulators of the hopping blocks' MMAs start from them (what the MMA of such a block leaves there).
+template <bool DIAG, bool SD = false> struct RowSum {
     double a10 = 0.0, a11 = 0.0, a20 = 0.0, a21 = 0.0, yr = 0.0, yi = 0.0;
     __device__ __forceinline__ void begin(const double2 &x0, double b0) {
+        if (SD && !DIAG) {
+            a10 = b0 * x0.x, a20 = b0 * x0.y;
+            return;
+        }
         dmma_8x8x4(a10, a11, x0.x, b0);
         dmma_8x8x4(a20, a21, x0.y, b0);
         if (DIAG) yr = a10 - a21, yi = a11 + a20;
@@ -118,10 +125,10 @@ template <bool DIAG> struct RowSum {
     }
 };
 
-template <bool DIAG>
+template <bool DIAG, bool SD = false>
 __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1, const double2 &x2, const double2 &x3,
                                             const double2 &x4, double b0, const double (&bop)[kDirs], double &yr, double &yi) {
-    RowSum<DIAG> r;
+    RowSum<DIAG, SD> r;
     r.begin(x0, b0);
     r.add(x1, bop[1]);
     r.add(x2, bop[2]);
@@ -174,7 +181,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // neighbours (and the T_n of [B]) two iterations later, and the T_{n+1} records it computes are its own operands of [B]
 // for three iterations -- so shared memory is read only for what OTHER warps own: 6 instead of 16 LDS.128 per warp and
 // iteration.  The shared-memory / L1 data pipe is what bounds the 8-warp shape.
-template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE, bool REG = false>
+template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE, bool REG = false, bool SD = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
@@ -288,7 +295,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         double fsA[S], fsB[S], fsN[S];  // SELF: on-site fragments of the planes of [A], [B] and of the next [A]
 #pragma unroll
         for (int s = 0; s < S; ++s) fsA[s] = fsB[s] = fsN[s] = 0.0;
-        if (SELF) self_fragments<S>(jvA, fsA, table, lane);
+        if (SELF) self_fragments<S, SD>(jvA, fsA, table, dtab, lane);
         // Global element of (plane x0 - 1, site ya): T_{n+1} / E_{j-1} / E_{j+1} of the warp's rows; only owned rows of
         // owned planes are dereferenced through it.  The second row sits 32 elements on.
         const ptrdiff_t gbase = ((ptrdiff_t)(x0 - 1) * wk.M + ya) * 32 + lane;
@@ -363,7 +370,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             cplane += plane_codes;
             cplane -= cplane >= all_codes ? all_codes : 0;
             if (code_lane && i < len) jn2 = __ldg(dcode + cplane + coff);
-            if (SELF) self_fragments<S>(jnext, fsN, table, lane);
+            if (SELF) self_fragments<S, SD>(jnext, fsN, table, dtab, lane);
             double2 tn[S] = {};  // T_n of the warp's rows in the plane of [B] = the records [A] reads as its x-1 neighbours
             double2 out[S] = {};  // T_{n+1} of the warp's rows in the plane of [A]
             // [B]: update, store and dot products of row s from its product (yr, yi) and its own T_{n+1} record
@@ -391,7 +398,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t nm = aN + (c & (kRingN - 1)) * PLANE_N;
                 const uint32_t n0 = aN + ((c + 1) & (kRingN - 1)) * PLANE_N;
                 const uint32_t np = aN + ((c + 2) & (kRingN - 1)) * PLANE_N;
-                hold_fragments<DIAG, SELF, S>(jvA, jheld, keep, table, dtab, lane, self_lane);
+                hold_fragments<DIAG, SELF, S, SD>(jvA, jheld, keep, table, dtab, lane, self_lane);
                 double2 c_[S + 2], q[S];  // c_[1 + s] = the own record of site s; c_[0], c_[S + 1] = the warp's in-plane neighbours
                 if (REG) {
                     c_[0] = lds_rec(n0 - R);
@@ -407,7 +414,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t t1 = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
                 // The newest plane (x+1 neighbours) feeds the LAST term of a row: its barrier is waited for only after the
                 // other four terms are under way (+1 %: profiles/r02/21_latewait.log).
-                RowSum<DIAG> rs[S];
+                RowSum<DIAG, SD> rs[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     rs[s].begin(c_[1 + s], SELF ? fsA[s] : keep[s][0]);
@@ -452,7 +459,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
                 const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
-                hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
+                hold_fragments<DIAG, SELF, S, SD>(jvB, jheld, keep, table, dtab, lane, self_lane);
                 double2 c_[S + 2], m[S], q[S];
                 if (REG) {
                     c_[0] = lds_rec(t0 - R);
@@ -470,7 +477,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double yr, yi;
-                    row_product<DIAG>(c_[1 + s], m[s], c_[s], c_[2 + s], q[s], SELF ? fsB[s] : keep[s][0], keep[s], yr, yi);
+                    row_product<DIAG, SD>(c_[1 + s], m[s], c_[s], c_[2 + s], q[s], SELF ? fsB[s] : keep[s][0], keep[s], yr, yi);
                     finish_b(s, yr, yi, c_[1 + s]);
                 }
             }
@@ -485,7 +492,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
                 const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
                 const uint32_t tp = a1 + (uint32_t)(i & (kRing - 1)) * PLANE_W;
-                hold_fragments<DIAG, SELF, S>(jvB, jheld, keep, table, dtab, lane, self_lane);
+                hold_fragments<DIAG, SELF, S, SD>(jvB, jheld, keep, table, dtab, lane, self_lane);
                 double2 own[S], m[S], q[S];
                 if (REG) {
 #pragma unroll
@@ -498,7 +505,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
                     for (int s = 0; s < S; ++s) q[s] = lds_rec(tp + (uint32_t)s * R);
                 }
-                RowSum<DIAG> r0, r1;
+                RowSum<DIAG, SD> r0, r1;
                 r0.begin(own[0], SELF ? fsB[0] : keep[0][0]);
                 r1.begin(own[1], SELF ? fsB[1] : keep[1][0]);
                 r0.add(m[0], keep[0][1]);
@@ -619,7 +626,11 @@ pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ ci
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
                             double2 *, int, int, double, double, double, int, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S, int MINB, bool REG = false> PairKernel pick_pair_shape(bool diag, bool self, bool t2) {
+template <int NW, int S, int MINB, bool REG = false> PairKernel pick_pair_shape(bool diag, bool self, bool t2, bool sd = false) {
+    if (sd && !diag) {  // general hopping blocks, real-diagonal on-site blocks
+        if (self) return t2 ? cheb_pair_step<false, true, NW, S, MINB, 1, REG, true> : cheb_pair_step<false, true, NW, S, MINB, 0, REG, true>;
+        return t2 ? cheb_pair_step<false, false, NW, S, MINB, 1, REG, true> : cheb_pair_step<false, false, NW, S, MINB, 0, REG, true>;
+    }
     if (self) {
         if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1, REG> : cheb_pair_step<false, true, NW, S, MINB, 1, REG>;
         return diag ? cheb_pair_step<true, true, NW, S, MINB, 0, REG> : cheb_pair_step<false, true, NW, S, MINB, 0, REG>;
@@ -639,18 +650,18 @@ struct PairShape {
     size_t smem;
 };
 
-PairShape pair_shape(bool diag, bool self, bool t2) {
+PairShape pair_shape(bool diag, bool self, bool t2, bool sd) {
     PairShape s;
     // 8 warps x 2 sites: two CTAs per SM, one computes while the other waits at its barrier.  The shape
     // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
     // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
     const int warps = env_int("BDG_PAIR_WARPS", 8);
     if (warps <= 8)
-        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2);
+        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2, sd);
     else if (warps <= 12)  // one CTA per SM, 168 registers: the warp's own records stay in registers (REG)
-        s.warps = 12, s.sites = 2, s.kernel = pick_pair_shape<12, 2, 1, true>(diag, self, t2);
+        s.warps = 12, s.sites = 2, s.kernel = pick_pair_shape<12, 2, 1, true>(diag, self, t2, sd);
     else
-        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2);
+        s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2, sd);
     const int W = s.warps * s.sites;
     s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * (kRingN + 1);
     return s;
@@ -659,6 +670,9 @@ PairShape pair_shape(bool diag, bool self, bool t2) {
 // On-site fragments per row straight from the table (SELF) when the dictionary is large: then the on-site blocks
 // differ from site to site (disorder, a self-consistent gap, a phase winding) and holding them in registers from
 // plane to plane would reload them on every row through the slow path.
+// Real-diagonal on-site blocks next to general hopping blocks: two multiplications instead of two MMAs (BDG_ELL_SD=0: off)
+bool pair_sd(const EllDev &e) { return e.self_diag_usable && !e.diag_usable && env_int("BDG_ELL_SD", 1) != 0; }
+
 bool pair_self(const EllDev &e) {
     const int forced = env_int("BDG_PAIR_SELF", -1);
     return forced >= 0 ? forced != 0 : e.n_unique > 64;
@@ -703,7 +717,7 @@ int pair_probe(bdg_system *sys) {
 int pair_configure(bdg_system *sys) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), st.t2);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), st.t2, pair_sd(e));
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
@@ -743,7 +757,7 @@ int pair_configure(bdg_system *sys) {
 int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_next1, void *x_next2, double *dots_step) {
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), false);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), false, pair_sd(e));
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev),
@@ -759,7 +773,7 @@ int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double
     ChebState &st = sys->cheb;
     if (st.cube) return cube_launch(sys, first, x_cur, x_io, dots_step);
     const EllDev &e = sys->ell;
-    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), true);
+    const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), true, pair_sd(e));
     dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
     shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_io),

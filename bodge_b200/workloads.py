@@ -207,6 +207,8 @@ CONFIGS = {
                       label="CubicLattice((1000,1000,1)) every block distinct (random on-site terms and random Hermitian hopping)"),
     "C5_periodic": dict(shape=(1000, 1000, 1), build=lambda shape: junction(shape, periodic=True),
                         label="CubicLattice((1000,1000,1)) junction on a torus (the reference's periodic edges filled in)"),
+    "C5_dwave": dict(shape=(1000, 1000, 1), build=dwave_rashba,
+                     label="CubicLattice((1000,1000,1)) d-wave + Rashba (C3's model at 10^6 sites: complex hopping blocks, real-diagonal on-site blocks)"),
     "C5_bilayer": dict(shape=(1024, 1024, 1), build=benchmark_bilayer,
                        label="CubicLattice((1024,1024,1)) S/F bilayer with phase winding (the reference's misc/benchmark.py model)"),
 }

@@ -17,7 +17,7 @@ from util import rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-def _periodic(api, shape, *, x=True, y=True, random_hop=False, seed=3, disorder=False):
+def _periodic(api, shape, *, x=True, y=True, random_hop=False, seed=3, disorder=False, onsite_pairing=True):
     """README-type s-wave system on a 2-D lattice with the reference's periodic edges filled in
     (bodge/lattice.py:161-197; tests/test_hamiltonian.py:17-57 fills them with random matrices): wrap-around
     bonds along x and / or the in-plane axis.  ``random_hop``: one of three random complex 2x2 matrices per bond
@@ -37,7 +37,8 @@ def _periodic(api, shape, *, x=True, y=True, random_hop=False, seed=3, disorder=
         for i in lattice.sites():
             mu, ds = (3.0 + 0.4 * rng.random(), 0.1 + 0.2 * rng.random()) if disorder else (3.0, 0.2)
             H[i, i] = mu * api.σ0 - 0.05 * api.σ3
-            D[i, i] = -ds * api.jσ2
+            if onsite_pairing:   # without it the on-site blocks are real-diagonal: two multiplications instead of two MMAs (SD)
+                D[i, i] = -ds * api.jσ2
         pairs = list(lattice.bonds())
         if x:
             pairs += list(lattice.edges(axis=0))
@@ -70,6 +71,10 @@ SYSTEMS = {
     "torus_random_hop_7_19_1": (lambda api: _periodic(api, (7, 19, 1), random_hop=True), False),
     "torus_disordered_10_16_1": (lambda api: _periodic(api, (10, 16, 1), disorder=True), True),   # > 64 distinct blocks: SELF path
     "open_disordered_12_33_1": (lambda api: _periodic(api, (12, 33, 1), x=False, y=False, disorder=True, random_hop=True), False),
+    # general hopping blocks, real-diagonal on-site blocks (SD): held fragments / streamed per row (> 64 distinct blocks)
+    "torus_normal_random_hop_8_17_1": (lambda api: _periodic(api, (8, 17, 1), random_hop=True, onsite_pairing=False), False),
+    "open_normal_disordered_11_20_1": (lambda api: _periodic(api, (11, 20, 1), x=False, y=False, disorder=True, random_hop=True,
+                                                             onsite_pairing=False), False),
 }
 
 # (BDG_PAIR_SEG, BDG_PAIR_P, BDG_PAIR_WARPS): None = planner's choice
@@ -206,9 +211,17 @@ def test_auto_prefers_pair_where_it_is_faster(gpu_api, monkeypatch):
     flat.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
     assert flat.cheb_format()["kernel"] == "dict_diag"
     monkeypatch.delenv("BDG_AUTO_PAIR")
-    dwave = cases.dwave_rashba(gpu_api, (9, 8, 1))._sys          # complex hopping blocks: DMMA rows
+    dwave = cases.dwave_rashba(gpu_api, (9, 8, 1))._sys          # complex hopping blocks (MMA rows), real-diagonal on-site blocks (SD)
     dwave.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
-    assert dwave.cheb_format()["kernel"] == "dict"
+    assert dwave.cheb_format()["kernel"] == "pair"
+    pwave = _periodic(gpu_api, (9, 8, 1), x=False, y=False, random_hop=True)._sys   # complex hopping AND on-site pairing: ten MMAs per row
+    pwave.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
+    assert pwave.cheb_format()["kernel"] == "pair"
+    monkeypatch.setenv("BDG_AUTO_PAIR", "0")
+    pwave.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
+    assert pwave.cheb_format()["kernel"] == "dict"
+    monkeypatch.delenv("BDG_AUTO_PAIR")
+    pwave.cheb_end()
     cube = cases.swave_3d(gpu_api, (6, 5, 4))._sys
     cube.cheb_begin(n_random=8, seed=1, scale=scale, kernel="auto")
     assert cube.cheb_format()["kernel"] == "dict_diag"
@@ -237,7 +250,7 @@ def test_one_call_c_entry_point(gpu_api):
 
     lib = _native.load()
     for system, want_kernel in ((cases.junction(gpu_api, (30, 40, 1)), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag"),
-                                (cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict")):
+                                (cases.dwave_rashba(gpu_api, (9, 8, 1)), "t2")):
         H = system.matrix("bsr")
         scale = system.spectral_bound()
         x0 = orc.rademacher(77, H.shape[0], np.arange(8) + 2)
@@ -379,9 +392,10 @@ def test_t2_observables_and_auto_moments(gpu_api):
     F = system.free_energy(0.1, cuda=True, vectors=16, moments=512)
     assert system._sys.cheb_format()["kernel"] == "t2"
     assert abs(F - system.free_energy(0.1, cuda=True, vectors=16, moments=512, kernel="dict_diag")) <= 1e-10 * abs(F)
-    # where no two-applications-per-pass kernel applies or pays, auto_moments is plain auto (complex hopping blocks; small
+    # where no two-applications-per-pass kernel applies or pays, auto_moments is plain auto (no dictionary / no such lattice; small
     # three-dimensional lattices -- large ones have their own even-vector kernel: tests/test_gpu_cube.py)
-    for other, want in ((cases.dwave_rashba(gpu_api, (9, 8, 1)), "dict"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag")):
+    for other, want in ((_periodic(gpu_api, (9, 8, 1), x=False, y=False, random_hop=True), "t2"), (cases.swave_3d(gpu_api, (6, 5, 4)), "dict_diag"),
+                        (cases.dwave_rashba(gpu_api, (9, 8, 1)), "t2")):
         other.chebyshev_moments(16, vectors=8, seed=1)
         assert other._sys.cheb_format()["kernel"] == want
     system.chebyshev_moments(16, vectors=4, seed=1)
