@@ -124,8 +124,9 @@ int bdg_norm_inf(bdg_t *sys, double *norm);
  *      matrix("bsr"), consumers = free_energy / ldos, bodge/hamiltonian.py:253-387) --------- */
 enum { BDG_X0_PROBE = 0, BDG_X0_RADEMACHER = 1 };
 enum { BDG_MU_PER_COLUMN = 0, BDG_MU_SUM = 1 };
-/* AUTO = PAIR where its DFMA variant applies (DICT_DIAG matrix, open 2-D stencil, >= 5 columns), else DICT_DIAG,
- *        else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+/* AUTO = PAIR where it applies (DICT / DICT_DIAG matrix, nearest-neighbour stencil on a lattice with one-dimensional
+ *        x-planes, >= 5 columns), else DICT_DIAG, else DICT, else ELL -- the first the matrix qualifies for -- else DMMA.
+ *        BDG_AUTO_PAIR=0 in the environment keeps AUTO / AUTO_MOMENTS on the single-step kernels.
  * AUTO_MOMENTS = AUTO for callers that only read moments / observables (never T_{n-1}): T2 where PAIR would be
  *        chosen, else as AUTO.  bdg_cheb_moments and the Python observables use it;
  * T2   = the even-vector ("doubled argument") recursion E_{j+1} = 2 T_2(H~) E_j - E_{j-1}, E_j = T_2j(H~) x, on the
