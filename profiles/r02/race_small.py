@@ -10,7 +10,10 @@ import test_gpu_pair as t
 from oracle import bdg_oracle as orc
 
 api = types.SimpleNamespace(CubicLattice=b.CubicLattice, Hamiltonian=b.Hamiltonian, σ0=b.σ0, σ1=b.σ1, σ2=b.σ2, σ3=b.σ3, jσ2=b.jσ2, dwave=b.dwave)
-for name, kw in (("torus", dict(shape=(5, 7, 1))), ("torus disordered", dict(shape=(6, 9, 1), disorder=True)), ("open", dict(shape=(4, 1, 11), x=False, y=False))):
+for name, kw in (("torus", dict(shape=(5, 7, 1))), ("torus disordered", dict(shape=(6, 9, 1), disorder=True)), ("open", dict(shape=(4, 1, 11), x=False, y=False)),
+                 # MMA rows with real-diagonal on-site blocks (SD): held / streamed per row
+                 ("torus normal random hop", dict(shape=(5, 8, 1), random_hop=True, onsite_pairing=False)),
+                 ("open normal disordered", dict(shape=(6, 9, 1), x=False, y=False, disorder=True, random_hop=True, onsite_pairing=False))):
     shape = kw.pop("shape")
     system = t._periodic(api, shape, **kw)
     H = system.matrix("bsr")
