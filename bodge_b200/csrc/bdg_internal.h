@@ -79,6 +79,7 @@ struct RowWalk {
 // P owned sites; an item = (patch, segment of seg_len consecutive x), handed out segment-major.
 struct PairWalk {
     int Lx = 1, M = 1;
+    int open = 0;  // the plane has open ends (no in-plane wrap-around block): the rim patches own their rim site
     int P = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
 };
@@ -150,6 +151,7 @@ struct EllDev {
     // Two-steps-per-pass kernel (cheb_pair.cu): dictionary format + nearest-neighbour stencil on a
     // lattice whose x-planes are one-dimensional (pair_M sites per plane).
     bool pair_usable = false;
+    bool pair_open = false;  // no block wraps around in-plane
     int pair_M = 0;
     DevBuf dcode;  // int32 [n_sites][5]: dictionary code per stencil direction (self, x-1, y-1, y+1, x+1), -1 = none
     // ... and its three-dimensional sibling (cheb_cube.cu): open nearest-neighbour stencil on a lattice with Ly, Lz >= 2.

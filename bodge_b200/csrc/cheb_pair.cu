@@ -238,14 +238,19 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
         const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
-        const int y0 = patch * wk.P, x0 = seg * wk.seg_len, len = min(wk.Lx, x0 + wk.seg_len) - x0;
+        // Local site l = 1 of a patch is y0.  On a plane with OPEN ends (wk.open: no block wraps around in-plane) the site
+        // below the first patch / above the last one does not exist, so those two patches own their rim site too (l = 0 resp.
+        // l = P + 1) instead of recomputing a halo value nobody needs: n P + 2 sites in n patches (100 sites: 7 instead of 8).
+        const int y0 = patch * wk.P + wk.open, x0 = seg * wk.seg_len, len = min(wk.Lx, x0 + wk.seg_len) - x0;
+        const int own_lo = wk.open && patch == 0 ? 0 : 1, own_hi = wk.P + (wk.open && patch == wk.n_patches - 1 ? 1 : 0);
         const int n_planes = len + 4;  // T_n planes x0 - 2 .. x0 + len + 1 (mod Lx); plane t -> ring slot (cnt + t) % kRingN
-        // In-plane run of a T_n plane: y = y0 - 2 .. ye + 1 (ye = end of the owned sites), l2 = y - (y0 - 2); the part
-        // below 0 / from M on comes from the opposite side of the plane (its own small bulk copy).
-        const int ye = min(wk.M, y0 + wk.P), span = ye - y0 + 4;
-        const int n_lo = max(0, 2 - y0), n_hi = max(0, ye + 2 - wk.M);
+        // In-plane run of a T_n plane: y = y0 - 2 .. ye + 1 (ye = end of the owned sites; at most the W + 2 records of a ring
+        // plane), l2 = y - (y0 - 2); the part below 0 / from M on comes from the opposite side of the plane (its own small
+        // bulk copy).
+        const int ye = min(wk.M, y0 + own_hi), span = min(ye - y0 + 4, W + 2);
+        const int n_lo = max(0, 2 - y0), n_hi = max(0, y0 - 2 + span - wk.M);
         const double2 *src_lo = tb + (ptrdiff_t)(y0 - 2 + wk.M) * 32, *src_main = tb + (ptrdiff_t)(y0 - 2 + n_lo) * 32,
-                      *src_hi = tb + (ptrdiff_t)(ye + 2 - n_hi - wk.M) * 32;
+                      *src_hi = tb + (ptrdiff_t)(y0 - 2 + span - n_hi - wk.M) * 32;
         // One elected thread stages a plane: expect the bytes on the slot's barrier, then up to three bulk copies.
         auto issue = [&](int t) {
             if (warp == 0 && t < n_planes) {
@@ -277,7 +282,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         const int ya = y0 - 1 + l0;
         bool owned[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) owned[s] = l0 + s >= 1 && l0 + s <= wk.P && ya + s < wk.M;
+        for (int s = 0; s < S; ++s) owned[s] = l0 + s >= own_lo && l0 + s <= own_hi && ya + s < wk.M;
         // code index of this lane's (row, direction) in plane 0; rows past the halo (ragged patch) wrap anywhere valid
         int yl = (ya + csite) % wk.M;
         yl += yl < 0 ? wk.M : 0;
@@ -606,9 +611,10 @@ pair_check(int64_t n_slots, int width, int Lx, int M, const int32_t *__restrict_
 // Slot 0 of the fixed-width copy is the diagonal block; padding slots point at the row itself.
 __global__ void __launch_bounds__(256)
 pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ cidx, const int32_t *__restrict__ ccode,
-           int32_t *__restrict__ dcode) {
+           int32_t *__restrict__ dcode, int *__restrict__ wraps /* set to 1 when a block wraps around in-plane */) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_sites) return;
+    const int y = row % M;
     int out[kDirs] = {-1, -1, -1, -1, -1};
     for (int u = 0; u < width; ++u) {
         const int c = ccode[(size_t)row * width + u];
@@ -621,6 +627,7 @@ pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ ci
     }
 #pragma unroll
     for (int k = 0; k < kDirs; ++k) dcode[(size_t)row * kDirs + k] = out[k];
+    if ((y == 0 && out[2] >= 0) || (y == M - 1 && out[3] >= 0)) *wraps = 1;
 }
 
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
@@ -707,8 +714,13 @@ int pair_probe(bdg_system *sys) {
     if (e.pair_usable) {
         BDG_TRY(dev_alloc(sys, e.dcode, (size_t)e.n_sites * kDirs * sizeof(int32_t)));
         pair_codes<<<(unsigned)ceil_div(e.n_sites, 256), 256, 0, sys->stream>>>((int)e.n_sites, e.width, Lx, M, e.idx.as<int32_t>(),
-                                                                              e.code.as<int32_t>(), e.dcode.as<int32_t>());
+                                                                              e.code.as<int32_t>(), e.dcode.as<int32_t>(), bad);
         BDG_CUDA(cudaGetLastError());
+        // (`bad` is 0 here.)  Open plane ends let the rim patches own their rim site; the flag stays valid under incremental
+        // updates, which cannot add a block (a changed zero pattern rebuilds everything).
+        BDG_CUDA(cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, sys->stream));
+        BDG_CUDA(cudaStreamSynchronize(sys->stream));
+        e.pair_open = host == 0;
     }
     return BDG_OK;
 }
@@ -727,10 +739,12 @@ int pair_configure(bdg_system *sys) {
     w.Lx = sys->cubic[0];
     w.M = e.pair_M;
     const int p_max = shape.warps * shape.sites - 2;
-    const int n_patches_min = (int)ceil_div(w.M, p_max);
-    w.P = (int)ceil_div(w.M, n_patches_min);  // balanced patches
+    w.open = e.pair_open && env_int("BDG_PAIR_OPEN", 1) != 0 ? 1 : 0;
+    const int to_cover = std::max(1, w.M - 2 * w.open);  // n patches own n P (+ 2: the rim sites of a plane with open ends) sites
+    const int n_patches_min = (int)ceil_div(to_cover, p_max);
+    w.P = (int)ceil_div(to_cover, n_patches_min);  // balanced patches
     w.P = std::max(1, std::min(env_int("BDG_PAIR_P", w.P), p_max));
-    w.n_patches = (int)ceil_div(w.M, w.P);
+    w.n_patches = (int)ceil_div(to_cover, w.P);
     // Segment length: every item recomputes one plane of T_{n+1} on either side of its segment and
     // starts with a cold pipeline (about two more plane times); many items balance the CTAs.
     double best = -1.0;
