@@ -48,6 +48,30 @@ def test_packed_workloads_equal_dict_api(name, shape):
         assert same_bits(a, c)
 
 
+def test_periodic_junction_workload_fills_the_reference_edges():
+    """``junction(periodic=True)`` (bench / full-size test config C5_periodic) = the open junction plus ``-t σ0`` on every
+    periodic edge of the reference's skeleton (bodge/lattice.py:161-197): Hermitian, every block row complete."""
+    import bodge_b200 as b
+
+    for shape in ((9, 7, 1), (5, 1, 6), (4, 5, 3)):
+        lat = b.CubicLattice(shape)
+        open_ = [np.asarray(a) for a in workloads.junction(shape)]
+        per = [np.asarray(a) for a in workloads.junction(shape, periodic=True)]
+        extra = {(int(i), int(j)) for i, j in zip(per[0][len(open_[0]):], per[1][len(open_[1]):])}
+        want = set()
+        for axis in range(3):
+            if shape[axis] >= 3:
+                for i, j in lat.edges(axis=axis):
+                    want.add((lat.index(i), lat.index(j)))
+        assert extra == want and np.array_equal(per[0][:len(open_[0])], open_[0])
+        assert np.all(per[2][len(open_[2]):] == -1.0 * np.asarray(b.σ0))
+        (ptr, idx, data), _ = oracle_assemble(shape, [tuple(per)])
+        assert orc.hermitian_deviation(ptr, idx, data) == 0.0
+        kept = orc.eliminate_zeros(ptr, idx, data)[0]
+        n_axes = sum(1 for L in shape if L >= 3)
+        assert np.all(np.diff(kept) == 1 + 2 * n_axes + 2 * sum(1 for L in shape if L == 2))
+
+
 def test_kpm_postprocessing_matches_oracle():
     rng = np.random.default_rng(0)
     mu = rng.standard_normal(300) * np.exp(-np.arange(300) / 60.0)
