@@ -20,8 +20,9 @@
 //                     ahead; the result goes to a shared-memory ring (4 planes) and, for owned sites of owned planes,
 //                     to HBM;
 //                 __syncthreads; the plane [A] no longer needs is replaced by the plane eight ahead
-//                 [B] T_{n+2} of the plane one behind, for the owned sites, from the T_{n+1} ring's three planes and the
-//                     T_n records [A] read as its x-1 neighbours (kept in registers across the barrier).
+//                 [B] T_{n+2} of the plane one behind, for the owned sites, from the T_{n+1} ring's three planes -- of which
+//                     only the middle one, written an iteration ago, is read at other warps' sites -- and the T_n records
+//                     [A] read as its x-1 neighbours (kept in registers across the barrier).
 //
 // The halo T_{n+1} values (one site either side in y, one plane either side of the segment in x)
 // are recomputed, not exchanged: (P+2)/P x (len+2)/len redundant work on sub-step [A], no
@@ -52,6 +53,15 @@ namespace {
 constexpr int kRecBytes = 512;  // one site record at PW = 8: 8 columns x 4 components x complex128
 constexpr int kRing = 4;        // planes of the T_{n+1} ring (three read by [B], one being written)
 constexpr int kRingN = 8;       // planes of the T_n ring: three in use, five in flight (power of two)
+// Hand-over between the warps of a CTA: the __syncthreads between [A] and [B] (default); -DBDG_PAIR_LAZY = arrive at the end of an
+// iteration, wait after [A] of the next (see the loop: +2.8 % at burst clocks, -1 % under the sustained power cap: its 256
+// polling threads cost the clock what the slack gains; one poller per warp is 9 % slower; profiles/r02/54_* .. 58_*);
+// -DBDG_PAIR_SPLIT = the earlier split-phase experiment.
+#ifdef BDG_PAIR_LAZY
+constexpr int kRingGuard = 1;
+#else
+constexpr int kRingGuard = 0;
+#endif
 
 constexpr int kDirs = 5;  // direction-ordered row: self, x-1, y-1, y+1, x+1 (= ascending block column)
 
@@ -139,7 +149,7 @@ __device__ __forceinline__ void row_product(const double2 &x0, const double2 &x1
     yi = r.yi;
 }
 
-#ifdef BDG_PAIR_SPLIT
+#if defined(BDG_PAIR_SPLIT) || defined(BDG_PAIR_LAZY)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
@@ -190,7 +200,9 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                double *__restrict__ dots_step, const PairWalk wk) {
     // MODE 1: E_{j+1} = alpha2 H~u - (csub E_j + E_{j-1}); csub = 2, or 1 in the first launch, where E_{-1} is never loaded (= 0)
     constexpr int W = NW * S, R = kRecBytes;
-    constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = W * R;
+    // (lazy hand-over: one guard record behind every T_{n+1} plane -- the first / last warp's outer neighbour read, whose
+    // value never matters, must not land in the slot [A] is writing while [B] of the same iteration reads)
+    constexpr uint32_t PLANE_N = (W + 2) * R, PLANE_W = (W + kRingGuard) * R;
     extern __shared__ __align__(128) unsigned char pair_smem[];
     const uint32_t sTn = smem_u32(pair_smem);         // T_n planes, local site l2 = y - (y0 - 2)
     const uint32_t sT1 = sTn + kRingN * PLANE_N + R;  // guard record, then T_{n+1} planes (computed here), local site l = y - (y0 - 1)
@@ -213,7 +225,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the clears are ordered before the bulk copies
     __syncthreads();
     uint32_t cnt = 0;  // T_n planes consumed by the items before this one
-#ifdef BDG_PAIR_SPLIT
+#if defined(BDG_PAIR_SPLIT) || defined(BDG_PAIR_LAZY)
     uint32_t xphase = 0;  // parity of the hand-over barrier's current phase (one phase per iteration)
 #endif
     const size_t gstep = (size_t)wk.M * 32;
@@ -225,6 +237,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     uint32_t aN = sTn + (uint32_t)(l0 + 1) * R + (uint32_t)lane * 16u;
     uint32_t a1 = sT1 + (uint32_t)l0 * R + (uint32_t)lane * 16u;
     pin(aN), pin(a1);
+
     double keep[S][kDirs];
     int jheld = -2;
 #pragma unroll
@@ -456,10 +469,22 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
                 }
             }
 #ifndef BDG_PAIR_SPLIT
+#ifdef BDG_PAIR_LAZY
+            // What [B] of this iteration reads from OTHER warps is a plane old: the in-plane neighbours of T_{n+1}(x - 1), written
+            // in [A] of the previous iteration (the planes x - 2 and x it reads at the warp's own sites only).  So the CTA-wide
+            // hand-over it needs is the one of the PREVIOUS iteration: every thread arrives at the end of an iteration and waits
+            // for that phase only after [A] of the next one -- half an iteration of slack instead of none.
+            if (i >= 1) {
+                mbar_wait(sBar + 8 * kRingN, xphase);
+                xphase ^= 1u;
+                issue(i - 1 + kRingN);  // every warp is through [A] of iteration i - 1: plane i - 1 is dead
+            }
+#else
             __syncthreads();  // T_{n+1} of this plane complete in the ring
             // ... and [A] is done in every warp: plane i (its x-1 neighbours) is dead, its slot takes plane i + 8 -- seven
             // planes in flight beyond the one in use.
             issue(i + kRingN);
+#endif
             if (i >= 2) {
                 const uint32_t t0 = a1 + (uint32_t)((i - 1) & (kRing - 1)) * PLANE_W;
                 const uint32_t tm = a1 + (uint32_t)((i - 2) & (kRing - 1)) * PLANE_W;
@@ -534,6 +559,9 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
             }
             xphase ^= 1u;
 #endif
+#ifdef BDG_PAIR_LAZY
+            mbar_arrive(sBar + 8 * kRingN);  // this thread's T_{n+1} records of the plane are in the ring, its reads of older planes done
+#endif
             if (REG) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) o2[s] = o1[s], o1[s] = out[s];
@@ -544,6 +572,10 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 #pragma unroll
             for (int s = 0; s < S; ++s) fsB[s] = fsA[s], fsA[s] = fsN[s];
         }
+#ifdef BDG_PAIR_LAZY
+        mbar_wait(sBar + 8 * kRingN, xphase);  // the last iteration's phase: every arrival has its wait
+        xphase ^= 1u;
+#endif
         cnt += (uint32_t)n_planes;
     }
     }
@@ -670,7 +702,7 @@ PairShape pair_shape(bool diag, bool self, bool t2, bool sd) {
     else
         s.warps = 16, s.sites = 2, s.kernel = pick_pair_shape<16, 2, 1>(diag, self, t2, sd);
     const int W = s.warps * s.sites;
-    s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * W + 2) * kRecBytes + 8 * (kRingN + 1);
+    s.smem = ((size_t)kRingN * (W + 2) + (size_t)kRing * (W + kRingGuard) + 2) * kRecBytes + 8 * (kRingN + 1);
     return s;
 }
 
