@@ -82,6 +82,13 @@ struct PairWalk {
     int open = 0;  // the plane has open ends (no in-plane wrap-around block): the rim patches own their rim site
     int P = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
+    // Work lists (device, ChebState::work_items): CTA c works through pieces[cta_begin[c] .. cta_begin[c + 1]), a piece =
+    // (panel, patch, x0, len).  A maximal run of pieces of one panel inside a CTA is a "run": its dot products go to
+    // partials[run], runs are numbered in (panel, CTA) order, cta_run0[c] = first run of CTA c, and the runs of panel p are
+    // panel_runs[p] .. panel_runs[p + 1].
+    const int4 *pieces = nullptr;
+    const int *cta_begin = nullptr, *cta_run0 = nullptr, *panel_runs = nullptr;
+    int n_ctas = 0, n_runs = 0;
 };
 
 // Item grid of the two-applications-per-pass kernel for three-dimensional lattices (cheb_cube.cu): the (y, z) plane
@@ -121,6 +128,7 @@ struct ChebState {
     DevBuf tickets;   // uint32 [n_panels] arrival counters (last CTA reduces)
     DevBuf mu_tmp;    // staging for moment read-out
     DevBuf obs_tmp;   // staging for observables.cu (coefficients, energies, results)
+    DevBuf work_items;  // work lists of the two-step kernel (PairWalk)
     int grid_x = 0;
     int panels_per_group = 1;  // ELL kernel: panels sharing one pass over the matrix (grid.y = groups)
     int panel_batch = 1;       // ... of which this many have their loads in flight together

@@ -526,6 +526,7 @@ void cheb_release(bdg_system *sys) {
     dev_free(sys, st.tickets);
     dev_free(sys, st.mu_tmp);
     dev_free(sys, st.obs_tmp);
+    dev_free(sys, st.work_items);
     ell_release(sys);
     const int64_t launches = st.launches;
     st = ChebState();

@@ -41,8 +41,10 @@
 // [B] started on the warp's own records before the wait); run time: BDG_PAIR_WARPS=12 (REG: own records in registers,
 // one CTA per SM), =16; BDG_PAIR_SELF, BDG_PAIR_P, BDG_PAIR_SEG.
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
@@ -191,7 +193,66 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // neighbours (and the T_n of [B]) two iterations later, and the T_{n+1} records it computes are its own operands of [B]
 // for three iterations -- so shared memory is read only for what OTHER warps own: 6 instead of 16 LDS.128 per warp and
 // iteration.  The shared-memory / L1 data pipe is what bounds the 8-warp shape.
-template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE, bool REG = false, bool SD = false>
+// The four dot products of a run (= the pieces of one panel a CTA works through): quad -> warp -> CTA -> partials[run]; the
+// last run of a panel to arrive (runs r0 .. r1) adds the panel's partials up in a fixed order.  Called by all threads between
+// two pieces or at the end: the rings are idle and serve as scratch.
+template <int NW>
+__device__ __forceinline__ void flush_dots(double d0, double d1, double d2, double d3, unsigned char *scratch, int run, int r0, int r1,
+                                           int panel, int n_panels, double *__restrict__ partials, unsigned *__restrict__ tickets,
+                                           double *__restrict__ dots_step) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ bool is_last;
+    d0 += __shfl_xor_sync(kFull, d0, 1);
+    d1 += __shfl_xor_sync(kFull, d1, 1);
+    d2 += __shfl_xor_sync(kFull, d2, 1);
+    d3 += __shfl_xor_sync(kFull, d3, 1);
+    d0 += __shfl_xor_sync(kFull, d0, 2);
+    d1 += __shfl_xor_sync(kFull, d1, 2);
+    d2 += __shfl_xor_sync(kFull, d2, 2);
+    d3 += __shfl_xor_sync(kFull, d3, 2);
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(scratch);  // [NW][4][8], then comb [NW][32] behind it
+    double *comb = red + NW * 32;
+    if ((lane & 3) == 0) {
+        const int col = lane >> 2;
+        red[(warp * 4 + 0) * 8 + col] = d0;
+        red[(warp * 4 + 1) * 8 + col] = d1;
+        red[(warp * 4 + 2) * 8 + col] = d2;
+        red[(warp * 4 + 3) * 8 + col] = d3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[w * 32 + threadIdx.x];
+        partials[(size_t)run * 32 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == (unsigned)(r1 - r0 - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = r0 + warp; b < r1; b += NW) s += __ldcg(&partials[(size_t)b * 32 + lane]);
+        comb[warp * 32 + lane] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int g = 0; g < NW; ++g) t += comb[g * 32 + threadIdx.x];
+            // slot = which * 8 + column; which = (step within the pair) * 2 + (0: <T,T>, 1: <T',T>)
+            dots_step[(size_t)(threadIdx.x >> 3) * n_panels * 8 + panel * 8 + (threadIdx.x & 7)] = t;
+        }
+        if (threadIdx.x == 0) tickets[panel] = 0u;
+    }
+    __syncthreads();  // scratch and is_last are free again
+}
+
+// LISTED: the CTA's pieces come from the work lists of PairWalk (balanced plan, grid = (n_ctas, 1)); otherwise they are
+// computed from the item index (classic plan, grid = (CTAs per panel, panels)) -- kept as arithmetic on kernel parameters
+// because values loaded from memory leave the uniform datapath and the plane loop's predicates with them (+2 % time).
+template <bool DIAG, bool SELF, int NW, int S, int MINB, int MODE, bool REG = false, bool SD = false, bool LISTED = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xa /* T_{n-1} */, const double2 *__restrict__ xb /* T_n */,
@@ -209,10 +270,8 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const uint32_t sBar = sT1 + kRing * PLANE_W + R;  // guard record (halo rows of [B] read one before / past the ring), then one mbarrier per T_n slot
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int panel = blockIdx.y;
-    const size_t pbase = (size_t)panel * n_sites * 32;
-    const double2 *ta = xa + pbase, *tb = xb + pbase;
-    double2 *tc = xc + pbase, *td = xd + pbase;  // MODE 1: td = ta (E_{j+1} over E_{j-1}), tc unused
+    // LISTED: the panel of the pieces in hand and the run (= partial-sum slot) they belong to
+    int panel = -1, run = LISTED ? wk.cta_run0[blockIdx.x] : 0;
 
     for (uint32_t o = threadIdx.x * 16u; o < kRingN * PLANE_N + kRing * PLANE_W + 2 * R; o += NW * 32 * 16u)
         sts_rec(sTn + o, make_double2(0.0, 0.0));
@@ -249,12 +308,33 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const bool code_lane = lane < S * kDirs, self_lane = cdir == 0;
     const int plane_codes = wk.M * kDirs, all_codes = wk.Lx * plane_codes;
 
-    for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
-        const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
+    const int item0 = LISTED ? wk.cta_begin[blockIdx.x] : (int)blockIdx.x, item1 = LISTED ? wk.cta_begin[blockIdx.x + 1] : wk.n_items;
+    for (int item = item0; item < item1; item += LISTED ? 1 : (int)gridDim.x) {
+        int4 piece;  // panel, patch, x0, len
+        if (LISTED) {
+            piece = wk.pieces[item];
+            if (piece.x != panel) {
+                if (panel >= 0) {
+                    flush_dots<NW>(d0, d1, d2, d3, pair_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials,
+                                   tickets, dots_step);
+                    d0 = d1 = d2 = d3 = 0.0;
+                    ++run;
+                }
+                panel = piece.x;
+            }
+        } else {
+            const int seg = item / wk.n_patches;
+            piece.x = (int)blockIdx.y, piece.y = item - seg * wk.n_patches, piece.z = seg * wk.seg_len;
+            piece.w = min(wk.Lx, piece.z + wk.seg_len) - piece.z;
+        }
+        const size_t pbase = (size_t)piece.x * n_sites * 32;
+        const double2 *const ta = xa + pbase, *const tb = xb + pbase;
+        double2 *const tc = xc + pbase, *const td = xd + pbase;  // MODE 1: td = ta (E_{j+1} over E_{j-1}), tc unused
+        const int patch = piece.y;
         // Local site l = 1 of a patch is y0.  On a plane with OPEN ends (wk.open: no block wraps around in-plane) the site
         // below the first patch / above the last one does not exist, so those two patches own their rim site too (l = 0 resp.
         // l = P + 1) instead of recomputing a halo value nobody needs: n P + 2 sites in n patches (100 sites: 7 instead of 8).
-        const int y0 = patch * wk.P + wk.open, x0 = seg * wk.seg_len, len = min(wk.Lx, x0 + wk.seg_len) - x0;
+        const int y0 = patch * wk.P + wk.open, x0 = piece.z, len = piece.w;
         const int own_lo = wk.open && patch == 0 ? 0 : 1, own_hi = wk.P + (wk.open && patch == wk.n_patches - 1 ? 1 : 0);
         const int n_planes = len + 4;  // T_n planes x0 - 2 .. x0 + len + 1 (mod Lx); plane t -> ring slot (cnt + t) % kRingN
         // In-plane run of a T_n plane: y = y0 - 2 .. ye + 1 (ye = end of the owned sites; at most the W + 2 records of a ring
@@ -579,54 +659,14 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         cnt += (uint32_t)n_planes;
     }
     }
-
-    // ---- the four dot products of the two steps: quad -> warp -> CTA -> last CTA, fixed order ----
-    d0 += __shfl_xor_sync(kFull, d0, 1);
-    d1 += __shfl_xor_sync(kFull, d1, 1);
-    d2 += __shfl_xor_sync(kFull, d2, 1);
-    d3 += __shfl_xor_sync(kFull, d3, 1);
-    d0 += __shfl_xor_sync(kFull, d0, 2);
-    d1 += __shfl_xor_sync(kFull, d1, 2);
-    d2 += __shfl_xor_sync(kFull, d2, 2);
-    d3 += __shfl_xor_sync(kFull, d3, 2);
-    __syncthreads();  // the rings are dead: reuse them as reduction scratch
-    double *red = reinterpret_cast<double *>(pair_smem);  // [NW][4][8], then comb [NW][32] behind it
-    double *comb = red + NW * 32;
-    __shared__ bool is_last;
-    if ((lane & 3) == 0) {
-        const int col = lane >> 2;
-        red[(warp * 4 + 0) * 8 + col] = d0;
-        red[(warp * 4 + 1) * 8 + col] = d1;
-        red[(warp * 4 + 2) * 8 + col] = d2;
-        red[(warp * 4 + 3) * 8 + col] = d3;
+    if (LISTED) {
+        if (panel >= 0)
+            flush_dots<NW>(d0, d1, d2, d3, pair_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials, tickets,
+                           dots_step);
+    } else {
+        const int p = (int)blockIdx.y, r0 = p * (int)gridDim.x;
+        flush_dots<NW>(d0, d1, d2, d3, pair_smem, r0 + (int)blockIdx.x, r0, r0 + (int)gridDim.x, p, n_panels, partials, tickets, dots_step);
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += red[w * 32 + threadIdx.x];
-        partials[(size_t)(panel * gridDim.x + blockIdx.x) * 32 + threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    {
-        double s = 0.0;
-        for (unsigned b = warp; b < gridDim.x; b += NW) s += __ldcg(&partials[(size_t)(panel * gridDim.x + b) * 32 + lane]);
-        comb[warp * 32 + lane] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double t = 0.0;
-#pragma unroll
-        for (int g = 0; g < NW; ++g) t += comb[g * 32 + threadIdx.x];
-        // slot = which * 8 + column; which = (step within the pair) * 2 + (0: <T,T>, 1: <T',T>)
-        dots_step[(size_t)(threadIdx.x >> 3) * n_panels * 8 + panel * 8 + (threadIdx.x & 7)] = t;
-    }
-    if (threadIdx.x == 0) tickets[panel] = 0u;
 }
 
 // *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its four nearest
@@ -665,17 +705,18 @@ pair_codes(int n_sites, int width, int Lx, int M, const int32_t *__restrict__ ci
 using PairKernel = void (*)(const int32_t *, const double *, const double *, const double2 *, const double2 *, double2 *,
                             double2 *, int, int, double, double, double, int, double *, unsigned *, double *, const PairWalk);
 
-template <int NW, int S, int MINB, bool REG = false> PairKernel pick_pair_shape(bool diag, bool self, bool t2, bool sd = false) {
+template <int NW, int S, int MINB, bool REG = false, bool LISTED = false>
+PairKernel pick_pair_shape(bool diag, bool self, bool t2, bool sd = false) {
     if (sd && !diag) {  // general hopping blocks, real-diagonal on-site blocks
-        if (self) return t2 ? cheb_pair_step<false, true, NW, S, MINB, 1, REG, true> : cheb_pair_step<false, true, NW, S, MINB, 0, REG, true>;
-        return t2 ? cheb_pair_step<false, false, NW, S, MINB, 1, REG, true> : cheb_pair_step<false, false, NW, S, MINB, 0, REG, true>;
+        if (self) return t2 ? cheb_pair_step<false, true, NW, S, MINB, 1, REG, true, LISTED> : cheb_pair_step<false, true, NW, S, MINB, 0, REG, true, LISTED>;
+        return t2 ? cheb_pair_step<false, false, NW, S, MINB, 1, REG, true, LISTED> : cheb_pair_step<false, false, NW, S, MINB, 0, REG, true, LISTED>;
     }
     if (self) {
-        if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1, REG> : cheb_pair_step<false, true, NW, S, MINB, 1, REG>;
-        return diag ? cheb_pair_step<true, true, NW, S, MINB, 0, REG> : cheb_pair_step<false, true, NW, S, MINB, 0, REG>;
+        if (t2) return diag ? cheb_pair_step<true, true, NW, S, MINB, 1, REG, false, LISTED> : cheb_pair_step<false, true, NW, S, MINB, 1, REG, false, LISTED>;
+        return diag ? cheb_pair_step<true, true, NW, S, MINB, 0, REG, false, LISTED> : cheb_pair_step<false, true, NW, S, MINB, 0, REG, false, LISTED>;
     }
-    if (t2) return diag ? cheb_pair_step<true, false, NW, S, MINB, 1, REG> : cheb_pair_step<false, false, NW, S, MINB, 1, REG>;
-    return diag ? cheb_pair_step<true, false, NW, S, MINB, 0, REG> : cheb_pair_step<false, false, NW, S, MINB, 0, REG>;
+    if (t2) return diag ? cheb_pair_step<true, false, NW, S, MINB, 1, REG, false, LISTED> : cheb_pair_step<false, false, NW, S, MINB, 1, REG, false, LISTED>;
+    return diag ? cheb_pair_step<true, false, NW, S, MINB, 0, REG, false, LISTED> : cheb_pair_step<false, false, NW, S, MINB, 0, REG, false, LISTED>;
 }
 
 int env_int(const char *name, int fallback) {
@@ -686,6 +727,7 @@ int env_int(const char *name, int fallback) {
 struct PairShape {
     int warps, sites;  // NW, S
     PairKernel kernel;
+    PairKernel listed;  // the same kernel working through the lists of a balanced plan (8-warp shape only), else null
     size_t smem;
 };
 
@@ -695,8 +737,9 @@ PairShape pair_shape(bool diag, bool self, bool t2, bool sd) {
     // sweep (profiles/r01/s4_pair_shape_sweep.log: 16 x 2 one CTA per SM -2 %, 8 x 3 -11 %, 12 x 1 with 24
     // warps per SM -14 %, 6 x 2 with three CTAs per SM -15 %) left this one ahead; 16 x 2 is kept for the tests.
     const int warps = env_int("BDG_PAIR_WARPS", 8);
+    s.listed = nullptr;
     if (warps <= 8)
-        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2, sd);
+        s.warps = 8, s.sites = 2, s.kernel = pick_pair_shape<8, 2, 2>(diag, self, t2, sd), s.listed = pick_pair_shape<8, 2, 2, false, true>(diag, self, t2, sd);
     else if (warps <= 12)  // one CTA per SM, 168 registers: the warp's own records stay in registers (REG)
         s.warps = 12, s.sites = 2, s.kernel = pick_pair_shape<12, 2, 1, true>(diag, self, t2, sd);
     else
@@ -763,6 +806,7 @@ int pair_configure(bdg_system *sys) {
     const EllDev &e = sys->ell;
     const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), st.t2, pair_sd(e));
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
+    if (shape.listed) BDG_CUDA(cudaFuncSetAttribute(shape.listed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     int per_sm = 1;
     BDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape.kernel, shape.warps * 32, shape.smem));
     per_sm = std::max(per_sm, 1);
@@ -795,7 +839,84 @@ int pair_configure(bdg_system *sys) {
         }
         if (forced > 0) break;
     }
-    st.pair_grid_x = (int)std::min<int64_t>(slots, w.n_items);
+    // ---- classic or balanced plan ------------------------------------------------------------------------------------
+    // Classic: every panel has its own `gx` CTAs (grid = (gx, panels)), CTA (bx, panel) takes the items bx, bx + gx, ...
+    // (segment-major: the grid sweeps the lattice as one wavefront, so the halo sites of a patch are in L2 when its neighbour
+    // reads them); the kernel computes its items from the item index.
+    // Balanced: the (panel, patch, x) space cut into one contiguous chunk per CTA slot, handed to the kernel as lists -- no
+    // wave quantisation, no per-panel slot quantisation, fewer segment halos.  Taken when its longest CTA is clearly shorter
+    // (small lattices with many panels: C2 / C3: +3 .. +17 %); on large lattices the classic plan is near-perfect already.
+    constexpr int kPieceCost = 6;  // iterations a piece costs beyond its planes: two halo planes either side, cold pipeline
+    const int gx = (int)std::min<int64_t>(slots, w.n_items);
+    const int64_t all_slots = (int64_t)sys->sm_count * per_sm;
+    const double classic_cost = (double)ceil_div((int64_t)gx * st.n_panels, all_slots) * (double)ceil_div(w.n_items, gx) * (w.seg_len + kPieceCost);
+    w.pieces = nullptr, w.cta_begin = w.cta_run0 = w.panel_runs = nullptr;
+    w.n_ctas = gx, w.n_runs = gx * st.n_panels;
+    st.pair_grid_x = gx;
+    if (!shape.listed) return BDG_OK;
+    using Piece = std::array<int, 4>;
+    std::vector<std::vector<Piece>> plan;
+    double balanced_cost = 0.0;
+    {
+        const int64_t total = (int64_t)st.n_panels * w.n_patches * w.Lx;  // plane units, (panel, patch)-major
+        const int64_t chunk = std::max<int64_t>(16, ceil_div(total, all_slots));
+        const int64_t n_chunks = ceil_div(total, chunk);
+        int64_t begin = 0;
+        for (int64_t c = 1; c <= n_chunks; ++c) {
+            int64_t end = std::min(total, total * c / n_chunks);
+            const int64_t into = end % w.Lx;  // a cut close to a column boundary moves onto it (no sliver pieces)
+            if (c < n_chunks && into > 0 && into < 8) end -= into;
+            else if (c < n_chunks && into > w.Lx - 8) end += w.Lx - into;
+            if (end <= begin) continue;
+            std::vector<Piece> mine;
+            int64_t cost = 0;
+            for (int64_t u = begin; u < end;) {
+                const int64_t col = u / w.Lx;
+                const int x0 = (int)(u - col * w.Lx), len = (int)std::min<int64_t>(w.Lx - x0, end - u);
+                mine.push_back({(int)(col / w.n_patches), (int)(col % w.n_patches), x0, len});
+                cost += len + kPieceCost;
+                u += len;
+            }
+            balanced_cost = std::max(balanced_cost, (double)cost);
+            plan.push_back(std::move(mine));
+            begin = end;
+        }
+    }
+    const int force = env_int("BDG_PAIR_BALANCE", -1);
+    if (!(force >= 0 ? force != 0 : balanced_cost < 0.93 * classic_cost)) return BDG_OK;
+    // flat buffer: pieces (16-byte aligned: first), cta_begin, cta_run0, panel_runs
+    std::vector<int> flat;
+    std::vector<int> cta_begin{0}, cta_run0, panel_runs(st.n_panels + 1, 0);
+    int n_runs = 0;
+    for (const auto &mine : plan) {
+        cta_run0.push_back(n_runs);
+        int last_panel = -1;
+        for (const Piece &pc : mine) {
+            flat.insert(flat.end(), pc.begin(), pc.end());
+            if (pc[0] != last_panel) {
+                last_panel = pc[0];
+                panel_runs[pc[0] + 1] += 1;
+                n_runs += 1;
+            }
+        }
+        cta_begin.push_back((int)(flat.size() / 4));
+    }
+    for (int p = 0; p < st.n_panels; ++p) panel_runs[p + 1] += panel_runs[p];
+    const size_t o_begin = flat.size(), o_run0 = o_begin + cta_begin.size(), o_panel = o_run0 + cta_run0.size();
+    flat.insert(flat.end(), cta_begin.begin(), cta_begin.end());
+    flat.insert(flat.end(), cta_run0.begin(), cta_run0.end());
+    flat.insert(flat.end(), panel_runs.begin(), panel_runs.end());
+    BDG_TRY(dev_alloc(sys, st.work_items, flat.size() * sizeof(int)));
+    BDG_CUDA(cudaMemcpyAsync(st.work_items.ptr, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, sys->stream));
+    BDG_CUDA(cudaStreamSynchronize(sys->stream));  // `flat` goes out of scope
+    const int *base = st.work_items.as<int>();
+    w.pieces = reinterpret_cast<const int4 *>(base);
+    w.cta_begin = base + o_begin;
+    w.cta_run0 = base + o_run0;
+    w.panel_runs = base + o_panel;
+    w.n_ctas = (int)plan.size();
+    w.n_runs = n_runs;
+    st.pair_grid_x = (int)ceil_div(n_runs, st.n_panels);  // (sizes the partial-sum buffer: n_panels x pair_grid_x runs)
     return BDG_OK;
 }
 
@@ -804,8 +925,9 @@ int pair_launch(bdg_system *sys, const void *x_prev, const void *x_cur, void *x_
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
     const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), false, pair_sd(e));
-    dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
-    shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
+    const bool listed = st.pair_walk.pieces != nullptr;
+    dim3 grid((unsigned)st.pair_walk.n_ctas, listed ? 1u : (unsigned)st.n_panels);
+    (listed ? shape.listed : shape.kernel)<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_prev),
         static_cast<const double2 *>(x_cur), static_cast<double2 *>(x_next1), static_cast<double2 *>(x_next2),
         (int)e.n_sites, st.n_panels, 2.0 / st.scale, 0.0, 0.0, 0, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step,
@@ -820,8 +942,9 @@ int t2_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, double
     if (st.cube) return cube_launch(sys, first, x_cur, x_io, dots_step);
     const EllDev &e = sys->ell;
     const PairShape shape = pair_shape(st.kernel == BDG_KERNEL_DICT_DIAG, pair_self(e), true, pair_sd(e));
-    dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
-    shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
+    const bool listed = st.pair_walk.pieces != nullptr;
+    dim3 grid((unsigned)st.pair_walk.n_ctas, listed ? 1u : (unsigned)st.n_panels);
+    (listed ? shape.listed : shape.kernel)<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_io),
         static_cast<const double2 *>(x_cur), nullptr, static_cast<double2 *>(x_io), (int)e.n_sites, st.n_panels,
         1.0 / st.scale, (first ? 2.0 : 4.0) / st.scale, first ? 1.0 : 2.0, first ? 1 : 0, st.partials.as<double>(), st.tickets.as<unsigned>(),
