@@ -97,6 +97,10 @@ struct CubeWalk {
     int Lx = 1, Ly = 1, Lz = 1;
     int nPy = 1, nPz = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
+    // work lists of a balanced plan (see PairWalk), null for the classic plan
+    const int4 *pieces = nullptr;
+    const int *cta_begin = nullptr, *cta_run0 = nullptr, *panel_runs = nullptr;
+    int n_ctas = 0, n_runs = 0;
 };
 
 // ---- Chebyshev state ----------------------------------------------------------------------

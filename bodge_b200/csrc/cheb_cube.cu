@@ -43,6 +43,7 @@
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
 #include "cheb_smem.cuh"
+#include "work_lists.h"
 
 namespace {
 
@@ -116,10 +117,73 @@ __device__ __forceinline__ void hop(const double2 &x, double b, double &yr, doub
     yi = fma(b, x.y, yi);
 }
 
+// The four dot products of a run (cheb_pair.cu: flush_dots) on 4-column panels: components -> site halves -> warp -> CTA ->
+// partials[run]; the last run of a panel (runs r0 .. r1) adds them up in run order.
+template <int NW>
+__device__ __forceinline__ void flush_dots4(double d0, double d1, double d2, double d3, unsigned char *scratch, int run, int r0, int r1,
+                                            int panel, int n_panels, double *__restrict__ partials, unsigned *__restrict__ tickets,
+                                            double *__restrict__ dots_step) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ bool is_last;
+    d0 += __shfl_xor_sync(kFull, d0, 1);
+    d1 += __shfl_xor_sync(kFull, d1, 1);
+    d2 += __shfl_xor_sync(kFull, d2, 1);
+    d3 += __shfl_xor_sync(kFull, d3, 1);
+    d0 += __shfl_xor_sync(kFull, d0, 2);
+    d1 += __shfl_xor_sync(kFull, d1, 2);
+    d2 += __shfl_xor_sync(kFull, d2, 2);
+    d3 += __shfl_xor_sync(kFull, d3, 2);
+    d0 += __shfl_xor_sync(kFull, d0, 16);
+    d1 += __shfl_xor_sync(kFull, d1, 16);
+    d2 += __shfl_xor_sync(kFull, d2, 16);
+    d3 += __shfl_xor_sync(kFull, d3, 16);
+    __syncthreads();  // the rings are idle: reuse them as reduction scratch
+    double *red = reinterpret_cast<double *>(scratch);  // [NW][4 which][4 columns], then comb [NW][16]
+    double *comb = red + NW * 16;
+    if (lane < 16 && (lane & 3) == 0) {
+        const int col = lane >> 2;
+        red[(warp * 4 + 0) * 4 + col] = d0;
+        red[(warp * 4 + 1) * 4 + col] = d1;
+        red[(warp * 4 + 2) * 4 + col] = d2;
+        red[(warp * 4 + 3) * 4 + col] = d3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[w * 16 + threadIdx.x];
+        partials[(size_t)run * 16 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == (unsigned)(r1 - r0 - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (lane < 16) {
+            double s = 0.0;
+            for (int b = r0 + warp; b < r1; b += NW) s += __ldcg(&partials[(size_t)b * 16 + lane]);
+            comb[warp * 16 + lane] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            double t = 0.0;
+#pragma unroll
+            for (int g = 0; g < NW; ++g) t += comb[g * 16 + threadIdx.x];
+            // slot = which * 4 + column; which = (a, c, b, d) as in cheb_pair.cu
+            dots_step[(size_t)(threadIdx.x >> 2) * n_panels * 4 + panel * 4 + (threadIdx.x & 3)] = t;
+        }
+        if (threadIdx.x == 0) tickets[panel] = 0u;
+    }
+    __syncthreads();  // scratch and is_last are free again
+}
+
 // NW warps, one CTA per SM.  Body lists (one body = two z-adjacent sites): [A] the u region = the patch and its halo
 // ring without the corners -- rows 0 and PY + 1 of the region hold PZ / 2 bodies, the PY rows between (PZ + 2) / 2 --,
 // [B] the PY x PZ / 2 owned bodies; body b goes to warp b % NW.  At PY = PZ = 8, NW = 16: 48 + 32 bodies, three + two per warp.
-template <int NW, int PY, int PZ, int NE>
+// LISTED: the pieces come from the work lists of CubeWalk (balanced plan, grid = (n_ctas, 1)), else from the item index
+// (classic plan, grid = (CTAs per panel, panels)).
+template <int NW, int PY, int PZ, int NE, bool LISTED = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ table, const double *__restrict__ dtab,
                const double2 *__restrict__ xb /* E_j */, double2 *__restrict__ xio /* E_{j-1} -> E_{j+1} */, int n_sites,
@@ -140,10 +204,7 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool upper = lane >= 16;
     const int half = lane >> 4;
-    const int panel = blockIdx.y;
-    const size_t pbase = (size_t)panel * n_sites * 16;
-    const double2 *tb = xb + pbase;
-    double2 *tio = xio + pbase;
+    int panel = -1, run = LISTED ? wk.cta_run0[blockIdx.x] : 0;  // LISTED: the panel of the pieces in hand, their run
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -182,11 +243,32 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const bool code_lane = lane < 16 && (lane & 7) < 7;
     const int cs = lane >> 3, cu = lane & 7;  // code lanes: site of the pair, direction
 
-    for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
-        const int seg = item / wk.n_patches, patch = item - seg * wk.n_patches;
+    const int item0 = LISTED ? wk.cta_begin[blockIdx.x] : (int)blockIdx.x, item1 = LISTED ? wk.cta_begin[blockIdx.x + 1] : wk.n_items;
+    for (int item = item0; item < item1; item += LISTED ? 1 : (int)gridDim.x) {
+        int4 piece;  // panel, patch, x0, len
+        if (LISTED) {
+            piece = wk.pieces[item];
+            if (piece.x != panel) {
+                if (panel >= 0) {
+                    flush_dots4<NW>(d0, d1, d2, d3, cube_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials,
+                                    tickets, dots_step);
+                    d0 = d1 = d2 = d3 = 0.0;
+                    ++run;
+                }
+                panel = piece.x;
+            }
+        } else {
+            const int seg = item / wk.n_patches;
+            piece.x = (int)blockIdx.y, piece.y = item - seg * wk.n_patches, piece.z = seg * wk.seg_len;
+            piece.w = min(wk.Lx, piece.z + wk.seg_len) - piece.z;
+        }
+        const size_t pbase = (size_t)piece.x * n_sites * 16;
+        const double2 *const tb = xb + pbase;
+        double2 *const tio = xio + pbase;
+        const int patch = piece.y;
         const int py = patch / wk.nPz, pz = patch - py * wk.nPz;
         const int y0 = py * PY, z0 = pz * PZ;
-        const int x0 = seg * wk.seg_len, len = min(wk.Lx, x0 + wk.seg_len) - x0;
+        const int x0 = piece.z, len = piece.w;
         const int n_planes = len + 4;  // E_j planes x0 - 2 .. x0 + len + 1; those outside the lattice are not copied
 
         __syncthreads();  // every warp is done with the previous item's planes (all of them were waited for)
@@ -370,57 +452,14 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
         cnt += (uint32_t)n_planes;
     }
 
-    // ---- the four dot products: components -> site halves -> warp -> CTA -> last CTA, fixed order ----------------
-    d0 += __shfl_xor_sync(kFull, d0, 1);
-    d1 += __shfl_xor_sync(kFull, d1, 1);
-    d2 += __shfl_xor_sync(kFull, d2, 1);
-    d3 += __shfl_xor_sync(kFull, d3, 1);
-    d0 += __shfl_xor_sync(kFull, d0, 2);
-    d1 += __shfl_xor_sync(kFull, d1, 2);
-    d2 += __shfl_xor_sync(kFull, d2, 2);
-    d3 += __shfl_xor_sync(kFull, d3, 2);
-    d0 += __shfl_xor_sync(kFull, d0, 16);
-    d1 += __shfl_xor_sync(kFull, d1, 16);
-    d2 += __shfl_xor_sync(kFull, d2, 16);
-    d3 += __shfl_xor_sync(kFull, d3, 16);
-    __syncthreads();  // the rings are dead: reuse them as reduction scratch
-    double *red = reinterpret_cast<double *>(cube_smem);  // [NW][4 which][4 columns], then comb [NW][16]
-    double *comb = red + NW * 16;
-    __shared__ bool is_last;
-    if (lane < 16 && (lane & 3) == 0) {
-        const int col = lane >> 2;
-        red[(warp * 4 + 0) * 4 + col] = d0;
-        red[(warp * 4 + 1) * 4 + col] = d1;
-        red[(warp * 4 + 2) * 4 + col] = d2;
-        red[(warp * 4 + 3) * 4 + col] = d3;
+    if (LISTED) {
+        if (panel >= 0)
+            flush_dots4<NW>(d0, d1, d2, d3, cube_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials, tickets,
+                            dots_step);
+    } else {
+        const int p = (int)blockIdx.y, r0 = p * (int)gridDim.x;
+        flush_dots4<NW>(d0, d1, d2, d3, cube_smem, r0 + (int)blockIdx.x, r0, r0 + (int)gridDim.x, p, n_panels, partials, tickets, dots_step);
     }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += red[w * 16 + threadIdx.x];
-        partials[(size_t)(panel * gridDim.x + blockIdx.x) * 16 + threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&tickets[panel], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (lane < 16) {
-        double s = 0.0;
-        for (unsigned b = warp; b < gridDim.x; b += NW) s += __ldcg(&partials[(size_t)(panel * gridDim.x + b) * 16 + lane]);
-        comb[warp * 16 + lane] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        double t = 0.0;
-#pragma unroll
-        for (int g = 0; g < NW; ++g) t += comb[g * 16 + threadIdx.x];
-        // slot = which * 4 + column; which = (a, c, b, d) as in cheb_pair.cu
-        dots_step[(size_t)(threadIdx.x >> 2) * n_panels * 4 + panel * 4 + (threadIdx.x & 3)] = t;
-    }
-    if (threadIdx.x == 0) tickets[panel] = 0u;
 }
 
 // *bad = 1 unless every block column of the fixed-width copy is the row itself or one of its six nearest neighbours on
@@ -462,7 +501,7 @@ using CubeKernel = void (*)(const int32_t *, const double *, const double *, con
 struct CubeShape {
     int warps, py, pz, ne;
     int rounds;  // bodies per warp and iteration ([A] + [B])
-    CubeKernel kernel;
+    CubeKernel kernel, listed;  // classic plan / balanced plan (work lists)
     size_t smem;
 };
 
@@ -472,6 +511,7 @@ template <int NW, int PY, int PZ, int NE> CubeShape make_shape() {
     constexpr int NA = PZ + PY * (PZ + 2) / 2, NB = PY * PZ / 2;
     s.rounds = (NA + NW - 1) / NW + (NB + NW - 1) / NW;
     s.kernel = cheb_cube_step<NW, PY, PZ, NE>;
+    s.listed = cheb_cube_step<NW, PY, PZ, NE, true>;
     s.smem = (size_t)NE * (PY + 4) * (PZ + 4) * kRec4 + (size_t)kRingU * (PY + 2) * (PZ + 2) * kRec4 + 8 * NE;
     return s;
 }
@@ -549,7 +589,24 @@ int cube_configure(bdg_system *sys) {
     }
     const CubeShape shape = cube_shape(st.cube_shape);
     BDG_CUDA(cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
-    st.pair_grid_x = (int)std::min<int64_t>(slots, st.cube_walk.n_items);
+    BDG_CUDA(cudaFuncSetAttribute(shape.listed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
+    CubeWalk &w = st.cube_walk;
+    const int gx = (int)std::min<int64_t>(slots, w.n_items);
+    w.pieces = nullptr, w.cta_begin = w.cta_run0 = w.panel_runs = nullptr;
+    w.n_ctas = gx, w.n_runs = gx * st.n_panels;
+    st.pair_grid_x = gx;
+    // Balanced plan (cheb_pair.cu: pair_configure): one contiguous chunk of the (panel, patch, x) space per SM instead of
+    // whole patch columns -- C4 with 8 columns is 128 columns of 64 planes on 148 SMs.
+    constexpr int kPieceCost = 6;
+    const double classic_cost = (double)ceil_div((int64_t)gx * st.n_panels, (int64_t)sys->sm_count) * (double)ceil_div(w.n_items, gx) * (w.seg_len + kPieceCost);
+    const WorkPlan plan = balanced_plan(st.n_panels, w.n_patches, Lx, sys->sm_count, kPieceCost);
+    const int force = cube_env("BDG_CUBE_BALANCE", -1);
+    if (!(force >= 0 ? force != 0 : plan.longest < 0.93 * classic_cost)) return BDG_OK;
+    WorkLists lists;
+    BDG_TRY(upload_work_lists(sys, st.work_items, plan, st.n_panels, lists));
+    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.cta_run0 = lists.cta_run0, w.panel_runs = lists.panel_runs;
+    w.n_ctas = lists.n_ctas, w.n_runs = lists.n_runs;
+    st.pair_grid_x = (int)ceil_div(lists.n_runs, st.n_panels);  // (sizes the partial-sum buffer)
     return BDG_OK;
 }
 
@@ -558,8 +615,9 @@ int cube_launch(bdg_system *sys, bool first, const void *x_cur, void *x_io, doub
     ChebState &st = sys->cheb;
     const EllDev &e = sys->ell;
     const CubeShape shape = cube_shape(st.cube_shape);
-    dim3 grid((unsigned)st.pair_grid_x, (unsigned)st.n_panels);
-    shape.kernel<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
+    const bool listed = st.cube_walk.pieces != nullptr;
+    dim3 grid((unsigned)st.cube_walk.n_ctas, listed ? 1u : (unsigned)st.n_panels);
+    (listed ? shape.listed : shape.kernel)<<<grid, shape.warps * 32, shape.smem, sys->stream>>>(
         e.dcode3.as<int32_t>(), e.table.as<double>(), e.dtab.as<double>(), static_cast<const double2 *>(x_cur),
         static_cast<double2 *>(x_io), (int)e.n_sites, st.n_panels, 1.0 / st.scale, (first ? 2.0 : 4.0) / st.scale, first ? 1.0 : 2.0,
         first ? 1 : 0, st.partials.as<double>(), st.tickets.as<unsigned>(), dots_step, st.cube_walk);

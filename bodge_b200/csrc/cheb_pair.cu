@@ -49,6 +49,7 @@
 #include "bdg_internal.h"
 #include "cheb_device.cuh"
 #include "cheb_smem.cuh"
+#include "work_lists.h"
 
 namespace {
 
@@ -854,69 +855,14 @@ int pair_configure(bdg_system *sys) {
     w.n_ctas = gx, w.n_runs = gx * st.n_panels;
     st.pair_grid_x = gx;
     if (!shape.listed) return BDG_OK;
-    using Piece = std::array<int, 4>;
-    std::vector<std::vector<Piece>> plan;
-    double balanced_cost = 0.0;
-    {
-        const int64_t total = (int64_t)st.n_panels * w.n_patches * w.Lx;  // plane units, (panel, patch)-major
-        const int64_t chunk = std::max<int64_t>(16, ceil_div(total, all_slots));
-        const int64_t n_chunks = ceil_div(total, chunk);
-        int64_t begin = 0;
-        for (int64_t c = 1; c <= n_chunks; ++c) {
-            int64_t end = std::min(total, total * c / n_chunks);
-            const int64_t into = end % w.Lx;  // a cut close to a column boundary moves onto it (no sliver pieces)
-            if (c < n_chunks && into > 0 && into < 8) end -= into;
-            else if (c < n_chunks && into > w.Lx - 8) end += w.Lx - into;
-            if (end <= begin) continue;
-            std::vector<Piece> mine;
-            int64_t cost = 0;
-            for (int64_t u = begin; u < end;) {
-                const int64_t col = u / w.Lx;
-                const int x0 = (int)(u - col * w.Lx), len = (int)std::min<int64_t>(w.Lx - x0, end - u);
-                mine.push_back({(int)(col / w.n_patches), (int)(col % w.n_patches), x0, len});
-                cost += len + kPieceCost;
-                u += len;
-            }
-            balanced_cost = std::max(balanced_cost, (double)cost);
-            plan.push_back(std::move(mine));
-            begin = end;
-        }
-    }
+    const WorkPlan plan = balanced_plan(st.n_panels, w.n_patches, w.Lx, all_slots, kPieceCost);
     const int force = env_int("BDG_PAIR_BALANCE", -1);
-    if (!(force >= 0 ? force != 0 : balanced_cost < 0.93 * classic_cost)) return BDG_OK;
-    // flat buffer: pieces (16-byte aligned: first), cta_begin, cta_run0, panel_runs
-    std::vector<int> flat;
-    std::vector<int> cta_begin{0}, cta_run0, panel_runs(st.n_panels + 1, 0);
-    int n_runs = 0;
-    for (const auto &mine : plan) {
-        cta_run0.push_back(n_runs);
-        int last_panel = -1;
-        for (const Piece &pc : mine) {
-            flat.insert(flat.end(), pc.begin(), pc.end());
-            if (pc[0] != last_panel) {
-                last_panel = pc[0];
-                panel_runs[pc[0] + 1] += 1;
-                n_runs += 1;
-            }
-        }
-        cta_begin.push_back((int)(flat.size() / 4));
-    }
-    for (int p = 0; p < st.n_panels; ++p) panel_runs[p + 1] += panel_runs[p];
-    const size_t o_begin = flat.size(), o_run0 = o_begin + cta_begin.size(), o_panel = o_run0 + cta_run0.size();
-    flat.insert(flat.end(), cta_begin.begin(), cta_begin.end());
-    flat.insert(flat.end(), cta_run0.begin(), cta_run0.end());
-    flat.insert(flat.end(), panel_runs.begin(), panel_runs.end());
-    BDG_TRY(dev_alloc(sys, st.work_items, flat.size() * sizeof(int)));
-    BDG_CUDA(cudaMemcpyAsync(st.work_items.ptr, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, sys->stream));
-    BDG_CUDA(cudaStreamSynchronize(sys->stream));  // `flat` goes out of scope
-    const int *base = st.work_items.as<int>();
-    w.pieces = reinterpret_cast<const int4 *>(base);
-    w.cta_begin = base + o_begin;
-    w.cta_run0 = base + o_run0;
-    w.panel_runs = base + o_panel;
-    w.n_ctas = (int)plan.size();
-    w.n_runs = n_runs;
-    st.pair_grid_x = (int)ceil_div(n_runs, st.n_panels);  // (sizes the partial-sum buffer: n_panels x pair_grid_x runs)
+    if (!(force >= 0 ? force != 0 : plan.longest < 0.93 * classic_cost)) return BDG_OK;
+    WorkLists lists;
+    BDG_TRY(upload_work_lists(sys, st.work_items, plan, st.n_panels, lists));
+    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.cta_run0 = lists.cta_run0, w.panel_runs = lists.panel_runs;
+    w.n_ctas = lists.n_ctas, w.n_runs = lists.n_runs;
+    st.pair_grid_x = (int)ceil_div(lists.n_runs, st.n_panels);  // (sizes the partial-sum buffer: n_panels x pair_grid_x runs)
     return BDG_OK;
 }
 
