@@ -82,12 +82,11 @@ struct PairWalk {
     int open = 0;  // the plane has open ends (no in-plane wrap-around block): the rim patches own their rim site
     int P = 1, n_patches = 1;
     int seg_len = 1, n_segs = 1, n_items = 1;
-    // Work lists (device, ChebState::work_items): CTA c works through pieces[cta_begin[c] .. cta_begin[c + 1]), a piece =
-    // (panel, patch, x0, len).  A maximal run of pieces of one panel inside a CTA is a "run": its dot products go to
-    // partials[run], runs are numbered in (panel, CTA) order, cta_run0[c] = first run of CTA c, and the runs of panel p are
-    // panel_runs[p] .. panel_runs[p + 1].
+    // Work lists (device, ChebState::work_items; work_lists.h): CTA c works through pieces[cta_begin[c] .. cta_begin[c + 1]), a
+    // piece = (run, patch, x0, len).  A maximal sequence of pieces of one panel inside a CTA is a "run": its dot products go to
+    // partials[run]; run_panel[run] = its panel, and the runs of panel p are panel_runs[p] .. panel_runs[p + 1].
     const int4 *pieces = nullptr;
-    const int *cta_begin = nullptr, *cta_run0 = nullptr, *panel_runs = nullptr;
+    const int *cta_begin = nullptr, *run_panel = nullptr, *panel_runs = nullptr;
     int n_ctas = 0, n_runs = 0;
 };
 
@@ -99,7 +98,7 @@ struct CubeWalk {
     int seg_len = 1, n_segs = 1, n_items = 1;
     // work lists of a balanced plan (see PairWalk), null for the classic plan
     const int4 *pieces = nullptr;
-    const int *cta_begin = nullptr, *cta_run0 = nullptr, *panel_runs = nullptr;
+    const int *cta_begin = nullptr, *run_panel = nullptr, *panel_runs = nullptr;
     int n_ctas = 0, n_runs = 0;
 };
 

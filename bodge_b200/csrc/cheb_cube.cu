@@ -204,7 +204,7 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool upper = lane >= 16;
     const int half = lane >> 4;
-    int panel = -1, run = LISTED ? wk.cta_run0[blockIdx.x] : 0;  // LISTED: the panel of the pieces in hand, their run
+    int panel = -1, run = -1;  // LISTED: the panel of the pieces in hand, their run
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -247,16 +247,17 @@ cheb_cube_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     for (int item = item0; item < item1; item += LISTED ? 1 : (int)gridDim.x) {
         int4 piece;  // panel, patch, x0, len
         if (LISTED) {
-            piece = wk.pieces[item];
-            if (piece.x != panel) {
-                if (panel >= 0) {
+            piece = wk.pieces[item];  // (run, patch, x0, len)
+            if (piece.x != run) {
+                if (run >= 0) {
                     flush_dots4<NW>(d0, d1, d2, d3, cube_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials,
-                                    tickets, dots_step);
+                                   tickets, dots_step);
                     d0 = d1 = d2 = d3 = 0.0;
-                    ++run;
                 }
-                panel = piece.x;
+                run = piece.x;
+                panel = wk.run_panel[run];
             }
+            piece.x = panel;
         } else {
             const int seg = item / wk.n_patches;
             piece.x = (int)blockIdx.y, piece.y = item - seg * wk.n_patches, piece.z = seg * wk.seg_len;
@@ -592,19 +593,19 @@ int cube_configure(bdg_system *sys) {
     BDG_CUDA(cudaFuncSetAttribute(shape.listed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shape.smem));
     CubeWalk &w = st.cube_walk;
     const int gx = (int)std::min<int64_t>(slots, w.n_items);
-    w.pieces = nullptr, w.cta_begin = w.cta_run0 = w.panel_runs = nullptr;
+    w.pieces = nullptr, w.cta_begin = w.run_panel = w.panel_runs = nullptr;
     w.n_ctas = gx, w.n_runs = gx * st.n_panels;
     st.pair_grid_x = gx;
     // Balanced plan (cheb_pair.cu: pair_configure): one contiguous chunk of the (panel, patch, x) space per SM instead of
     // whole patch columns -- C4 with 8 columns is 128 columns of 64 planes on 148 SMs.
     constexpr int kPieceCost = 6;
     const double classic_cost = (double)ceil_div((int64_t)gx * st.n_panels, (int64_t)sys->sm_count) * (double)ceil_div(w.n_items, gx) * (w.seg_len + kPieceCost);
-    const WorkPlan plan = balanced_plan(st.n_panels, w.n_patches, Lx, sys->sm_count, kPieceCost);
+    const WorkPlan plan = best_balanced_plan(st.n_panels, w.n_patches, Lx, sys->sm_count, kPieceCost, 1.0);
     const int force = cube_env("BDG_CUBE_BALANCE", -1);
     if (!(force >= 0 ? force != 0 : plan.longest < 0.93 * classic_cost)) return BDG_OK;
     WorkLists lists;
     BDG_TRY(upload_work_lists(sys, st.work_items, plan, st.n_panels, lists));
-    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.cta_run0 = lists.cta_run0, w.panel_runs = lists.panel_runs;
+    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.run_panel = lists.run_panel, w.panel_runs = lists.panel_runs;
     w.n_ctas = lists.n_ctas, w.n_runs = lists.n_runs;
     st.pair_grid_x = (int)ceil_div(lists.n_runs, st.n_panels);  // (sizes the partial-sum buffer)
     return BDG_OK;

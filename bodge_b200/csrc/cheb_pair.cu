@@ -272,7 +272,7 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // LISTED: the panel of the pieces in hand and the run (= partial-sum slot) they belong to
-    int panel = -1, run = LISTED ? wk.cta_run0[blockIdx.x] : 0;
+    int panel = -1, run = -1;
 
     for (uint32_t o = threadIdx.x * 16u; o < kRingN * PLANE_N + kRing * PLANE_W + 2 * R; o += NW * 32 * 16u)
         sts_rec(sTn + o, make_double2(0.0, 0.0));
@@ -313,16 +313,17 @@ cheb_pair_step(const int32_t *__restrict__ dcode, const double *__restrict__ tab
     for (int item = item0; item < item1; item += LISTED ? 1 : (int)gridDim.x) {
         int4 piece;  // panel, patch, x0, len
         if (LISTED) {
-            piece = wk.pieces[item];
-            if (piece.x != panel) {
-                if (panel >= 0) {
+            piece = wk.pieces[item];  // (run, patch, x0, len)
+            if (piece.x != run) {
+                if (run >= 0) {
                     flush_dots<NW>(d0, d1, d2, d3, pair_smem, run, wk.panel_runs[panel], wk.panel_runs[panel + 1], panel, n_panels, partials,
                                    tickets, dots_step);
                     d0 = d1 = d2 = d3 = 0.0;
-                    ++run;
                 }
-                panel = piece.x;
+                run = piece.x;
+                panel = wk.run_panel[run];
             }
+            piece.x = panel;
         } else {
             const int seg = item / wk.n_patches;
             piece.x = (int)blockIdx.y, piece.y = item - seg * wk.n_patches, piece.z = seg * wk.seg_len;
@@ -851,16 +852,16 @@ int pair_configure(bdg_system *sys) {
     const int gx = (int)std::min<int64_t>(slots, w.n_items);
     const int64_t all_slots = (int64_t)sys->sm_count * per_sm;
     const double classic_cost = (double)ceil_div((int64_t)gx * st.n_panels, all_slots) * (double)ceil_div(w.n_items, gx) * (w.seg_len + kPieceCost);
-    w.pieces = nullptr, w.cta_begin = w.cta_run0 = w.panel_runs = nullptr;
+    w.pieces = nullptr, w.cta_begin = w.run_panel = w.panel_runs = nullptr;
     w.n_ctas = gx, w.n_runs = gx * st.n_panels;
     st.pair_grid_x = gx;
     if (!shape.listed) return BDG_OK;
-    const WorkPlan plan = balanced_plan(st.n_panels, w.n_patches, w.Lx, all_slots, kPieceCost);
+    const WorkPlan plan = best_balanced_plan(st.n_panels, w.n_patches, w.Lx, all_slots, kPieceCost, 1.08);
     const int force = env_int("BDG_PAIR_BALANCE", -1);
     if (!(force >= 0 ? force != 0 : plan.longest < 0.93 * classic_cost)) return BDG_OK;
     WorkLists lists;
     BDG_TRY(upload_work_lists(sys, st.work_items, plan, st.n_panels, lists));
-    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.cta_run0 = lists.cta_run0, w.panel_runs = lists.panel_runs;
+    w.pieces = lists.pieces, w.cta_begin = lists.cta_begin, w.run_panel = lists.run_panel, w.panel_runs = lists.panel_runs;
     w.n_ctas = lists.n_ctas, w.n_runs = lists.n_runs;
     st.pair_grid_x = (int)ceil_div(lists.n_runs, st.n_panels);  // (sizes the partial-sum buffer: n_panels x pair_grid_x runs)
     return BDG_OK;
