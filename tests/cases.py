@@ -196,5 +196,5 @@ def recorder_api():
         CubicLattice=lattice.CubicLattice,
         Hamiltonian=_RecordingHamiltonian,
         σ0=common.σ0, σ1=common.σ1, σ2=common.σ2, σ3=common.σ3, jσ2=common.jσ2,
-        dwave=helpers.dwave,
+        dwave=helpers.dwave, pwave=helpers.pwave,
     )

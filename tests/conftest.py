@@ -50,5 +50,5 @@ def gpu_api():
         pytest.fail("no CUDA device visible: the -m gpu tests must run on the GPU box")
     return types.SimpleNamespace(
         CubicLattice=b.CubicLattice, Hamiltonian=b.Hamiltonian,
-        σ0=b.σ0, σ1=b.σ1, σ2=b.σ2, σ3=b.σ3, jσ2=b.jσ2, dwave=b.dwave,
+        σ0=b.σ0, σ1=b.σ1, σ2=b.σ2, σ3=b.σ3, jσ2=b.jσ2, dwave=b.dwave, pwave=b.pwave,
     )
