@@ -13,6 +13,9 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 from beartype import beartype as typecheck
 from beartype.typing import Callable, Iterator
+# ... and the matrix containers handed to / returned from the public API, under the reference's alias names
+from scipy.sparse import bsr_matrix as BsrMatrix, coo_matrix as CooMatrix, csc_matrix as CscMatrix
+from scipy.sparse import csr_matrix as CsrMatrix, dia_matrix as DiaMatrix, spmatrix as SpMatrix
 
 # Lattice coordinates and flat indices.
 Index = int
@@ -20,35 +23,19 @@ Coord = tuple[int, int, int]
 Indices = tuple[Index, Index]
 Coords = tuple[Coord, Coord]
 
-# Matrix containers handed to / returned from the public API.
 Matrix = npt.NDArray[np.float64] | npt.NDArray[np.complex128]
-CooMatrix = sp.coo_matrix
-DiaMatrix = sp.dia_matrix
-BsrMatrix = sp.bsr_matrix
-CsrMatrix = sp.csr_matrix
-CscMatrix = sp.csc_matrix
-SpMatrix = sp.spmatrix
 
-π = np.pi
-pi = π
+pi = π = np.pi
 
 
 def _pauli(a, b, c, d) -> Matrix:
     return np.array([[a, b], [c, d]], dtype=np.complex128)
 
 
-# Spin matrices (identity + the three Pauli matrices) and their i-multiples.
-σ0: Matrix = _pauli(1, 0, 0, 1)
-σ1: Matrix = _pauli(0, 1, 1, 0)
-σ2: Matrix = _pauli(0, -1j, 1j, 0)
-σ3: Matrix = _pauli(1, 0, 0, -1)
-σ = np.stack([σ1, σ2, σ3])
-
-jσ0: Matrix = 1j * σ0
-jσ1: Matrix = 1j * σ1
-jσ2: Matrix = 1j * σ2
-jσ3: Matrix = 1j * σ3
-jσ = np.stack([jσ1, jσ2, jσ3])
+# Spin matrices (identity + the three Pauli matrices), their i-multiples, and the vectors (σ1, σ2, σ3), i(σ1, σ2, σ3).
+σ0, σ1, σ2, σ3 = _pauli(1, 0, 0, 1), _pauli(0, 1, 1, 0), _pauli(0, -1j, 1j, 0), _pauli(1, 0, 0, -1)
+jσ0, jσ1, jσ2, jσ3 = (1j * s for s in (σ0, σ1, σ2, σ3))
+σ, jσ = np.stack([σ1, σ2, σ3]), np.stack([jσ1, jσ2, jσ3])
 
 # ASCII spellings.
 sigma0, sigma1, sigma2, sigma3, sigma = σ0, σ1, σ2, σ3, σ
