@@ -372,7 +372,11 @@ class Hamiltonian:
         * T = 0 (the API default): ``g`` has a kink at the Fermi level, the series converges only algebraically --
           about 1e-7 relative at the default 8192 moments, 1e-4 in the worst cases -- and an ``AccuracyWarning``
           says so; use ``cuda=False`` or a small finite T when more is needed;
-        * an explicit ``moments`` below what ``tol`` asks for warns too.
+        * an explicit ``moments`` below what ``tol`` asks for warns too;
+        * EXACT zero modes: the trace counts every eigenvalue, so a pair of exactly-zero eigenvalues contributes its
+          ``-T ln 2``; the reference's ``ε > 0`` filter (hamiltonian.py:304) drops eigenvalues that LAPACK returns as
+          exactly 0.0 (sites nothing couples to) and keeps those it returns as ±1e-17 -- the two agree whenever no
+          eigenvalue is exactly zero.  A matrix that is identically zero returns the reference's 0.
 
         Multi-GPU: columns are sharded over the initialised ``torch.distributed`` group.
         """
@@ -386,6 +390,10 @@ class Hamiltonian:
             return float(-(1 / 2) * np.sum(ε) - T * S)
 
         scale = self.spectral_bound() if scale is None else float(scale)
+        if scale == 0.0:
+            # the matrix is identically zero (nothing set yet): no positive eigenvalue, the reference's sums over ε > 0
+            # are empty (hamiltonian.py:302-319) -- and there is no interval to map onto [-1, 1]
+            return 0.0
         need, reached = kpm.free_energy_moments(T, scale, tol)
         n_mom = need if moments is None else int(moments)
         if T == 0:
@@ -440,6 +448,11 @@ class Hamiltonian:
         eps = np.unique(np.abs(energies))
         if eps.size < 2:
             raise ValueError("need at least two distinct |energies| to define the broadening Γ")
+        if scale == 0.0:
+            # H = 0: every diagonal element of the resolvent is (ε + iΓ)^-1, what the reference's solve returns for it
+            rows = self._probe_rows(sites)  # (coordinates are validated like on the normal path)
+            g_imag = np.broadcast_to(np.imag(1.0 / (eps + 1j * np.gradient(eps))), (len(rows) // 4, 4, len(eps)))
+            return kpm.ldos_from_resolvent(g_imag, eps, energies)
         gamma_min = float(np.min(np.abs(np.gradient(eps))))
         need, reached = kpm.ldos_moments(scale, gamma_min, tol)
         moments = need if moments is None else int(moments)

@@ -60,3 +60,22 @@ def test_spin_valve_update_is_patched_in_place(gpu_api):
     physics_cases.spin_valve(gpu_api, types.SimpleNamespace(ldos=None, free_energy=free_energy))
     assert seen[1]["native_builds"] == seen[0]["native_builds"] == 1, seen
     assert seen[1]["patched_scatters"] == seen[0]["patched_scatters"] + 1, seen
+
+
+def test_observables_before_anything_is_set(gpu_api):
+    """A Hamiltonian with no entries (H = 0): the reference returns F = 0 (no positive eigenvalue) and the LDOS of the bare
+    resolvent (ε + iΓ)^-1; so does the CUDA path's front end, without a spectral interval to expand on."""
+    system = gpu_api.Hamiltonian(gpu_api.CubicLattice((6, 5, 1)))
+    assert system.spectral_bound() == 0.0
+    assert system.free_energy(0.1, cuda=True) == 0.0 == system.free_energy(0.1)
+    rho = system.ldos((2, 2, 0), [0.0, 0.1])
+    assert np.allclose(rho, [2 / (np.pi * 0.1), 2 * 0.1 / (np.pi * 0.02)], rtol=1e-15, atol=0)
+    # ... and once something is set the expansion takes over
+    lattice = system.lattice
+    with system as (H, D):
+        for i in lattice.sites():
+            H[i, i] = -1.5 * gpu_api.σ0
+        for i, j in lattice.bonds():
+            H[i, j] = -1.0 * gpu_api.σ0
+    F = system.free_energy(0.1)
+    assert system.spectral_bound() > 0 and abs(system.free_energy(0.1, cuda=True) - F) <= 1e-10 * abs(F)

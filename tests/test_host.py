@@ -293,3 +293,25 @@ def test_data_view_writes_through():
     sub[3, 3] = 5.0
     assert owner._sys.uploads[-1][2, 3, 3] == 5.0 and owner._sys.uploads[-1].shape == (3, 4, 4)
     assert isinstance(np.asarray(view), np.ndarray)
+
+
+def test_observables_of_an_all_zero_hamiltonian_follow_the_reference():
+    """Nothing set yet: ``spectral_bound()`` is 0, there is no interval to map onto [-1, 1] and no kernel runs -- the
+    reference's own answers for H = 0 are returned (empty sums over ε > 0: F = 0; resolvent (ε + iΓ)^-1: LDOS
+    2Γ / (π (ε² + Γ²)); checked against the unmodified reference when this was written).  Host logic only: the handle
+    is built without the device."""
+    import bodge_b200 as b
+    from bodge_b200.hamiltonian import Hamiltonian
+
+    lattice = b.CubicLattice((4, 3, 1))
+    system = object.__new__(Hamiltonian)
+    system.lattice, system.shape, system.device, system._scale_cache = lattice, (4 * lattice.size,) * 2, 0, 0.0
+    assert system.free_energy(0.1, cuda=True) == 0.0
+    energies = np.array([-0.2, 0.0, 0.1, 0.3])
+    eps = np.unique(np.abs(energies))
+    gamma = dict(zip(eps, np.gradient(eps)))
+    want = np.array([2 * gamma[abs(e)] / (np.pi * (e * e + gamma[abs(e)] ** 2)) for e in energies])
+    assert np.allclose(system.ldos((1, 1, 0), energies), want, rtol=1e-15, atol=0)
+    assert system.ldos_map([(0, 0, 0), (3, 2, 0)], energies).shape == (2, 4)
+    with pytest.raises(ValueError):
+        system.ldos((9, 9, 9), energies)
