@@ -306,6 +306,14 @@ class System:
         check(lib.bdg_export_csr(self._h, int(transpose), C.byref(nnz), _ptr(indptr), _ptr(indices), _ptr(data)))
         return indptr, indices, data
 
+    def zero_scalar_rows(self) -> int:
+        """Scalar rows of the 4N x 4N matrix without a single non-zero entry (the counting phase of ``bdg_export_csr``:
+        only the 4N + 1 row offsets come back)."""
+        nnz = C.c_int64()
+        indptr = np.empty(4 * self.n_sites + 1, dtype=np.int32)
+        check(load().bdg_export_csr(self._h, 0, C.byref(nnz), _ptr(indptr), None, None))
+        return int(np.count_nonzero(np.diff(indptr) == 0))
+
     def export_dense(self) -> np.ndarray:
         out = np.empty((4 * self.n_sites, 4 * self.n_sites), dtype=np.complex128)
         check(load().bdg_export_dense(self._h, _ptr(out)))

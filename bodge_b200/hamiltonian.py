@@ -373,10 +373,10 @@ class Hamiltonian:
           about 1e-7 relative at the default 8192 moments, 1e-4 in the worst cases -- and an ``AccuracyWarning``
           says so; use ``cuda=False`` or a small finite T when more is needed;
         * an explicit ``moments`` below what ``tol`` asks for warns too;
-        * EXACT zero modes: the trace counts every eigenvalue, so a pair of exactly-zero eigenvalues contributes its
-          ``-T ln 2``; the reference's ``ε > 0`` filter (hamiltonian.py:304) drops eigenvalues that LAPACK returns as
-          exactly 0.0 (sites nothing couples to) and keeps those it returns as ±1e-17 -- the two agree whenever no
-          eigenvalue is exactly zero.  A matrix that is identically zero returns the reference's 0.
+        * sites nothing couples to (a geometry cut out of the lattice by leaving sites unset): their rows are zero, LAPACK
+          returns their eigenvalues as exactly 0.0 and the reference's ``ε > 0`` filter (hamiltonian.py:304) drops them,
+          while a trace counts ``g(0) = -(T/2) ln 2`` for each.  The zero rows are counted on the device and their share
+          is taken out again, so the result is the reference's; a matrix that is identically zero returns 0 like it.
 
         Multi-GPU: columns are sharded over the initialised ``torch.distributed`` group.
         """
@@ -413,6 +413,8 @@ class Hamiltonian:
             return np.array([sysn.kpm_contract(coef, k, summed=True)])
 
         read.leading_dim = 1
+        # what the all-zero rows add to a trace and the reference leaves out (see the docstring); g(0) = 0 at T = 0
+        isolated = -0.5 * T * np.log(2.0) * self._sys.zero_scalar_rows() if T > 0 else 0.0
         if vectors is None:
             if self.shape[0] > (1 << 18):
                 # the reference's exact path (dense eigvalsh) stops being possible long before this size; the exact KPM
@@ -421,9 +423,9 @@ class Hamiltonian:
                               "columns (O(N^2) work); pass vectors=64 or so for a stochastic estimate (relative error "
                               "~ 1/sqrt(vectors * 4N))", AccuracyWarning, stacklevel=2)
             total = self._columns(n_mom, read, True, rows=np.arange(self.shape[0]), scale=scale, kernel=kernel)
-            return float(total[0])
+            return float(total[0] - isolated)
         total = self._columns(n_mom, read, True, vectors=vectors, seed=seed, scale=scale, kernel=kernel)
-        return float(total[0]) / vectors
+        return float(total[0] / vectors - isolated)   # (a Rademacher column has weight 1 on every row: the same share)
 
     @typecheck
     def ldos(self, site: Coord, energies: Matrix | list[float], *, moments: int | None = None,

@@ -79,3 +79,28 @@ def test_observables_before_anything_is_set(gpu_api):
             H[i, j] = -1.0 * gpu_api.σ0
     F = system.free_energy(0.1)
     assert system.spectral_bound() > 0 and abs(system.free_energy(0.1, cuda=True) - F) <= 1e-10 * abs(F)
+
+
+def test_sites_left_out_of_the_geometry(gpu_api):
+    """A geometry cut out of the lattice by leaving sites unset (here the two last columns): their rows are zero, the
+    reference's ``ε > 0`` filter drops their exactly-zero eigenvalues, and ``free_energy(cuda=True)`` takes their share
+    ``-(T/2) ln 2`` per row out of the trace again.  (Formula checked against the unmodified reference on the CPU:
+    oracle KPM + correction == reference to 2e-16 on this system.)"""
+    api = gpu_api
+    lattice = api.CubicLattice((6, 5, 1))
+    system = api.Hamiltonian(lattice)
+    with system as (H, D):
+        for i in lattice.sites():
+            if i[0] < 4:
+                H[i, i] = -1.5 * api.σ0
+                D[i, i] = 0.3 * api.jσ2
+        for i, j in lattice.bonds():
+            if i[0] < 4 and j[0] < 4:
+                H[i, j] = -1.0 * api.σ0
+    assert system._sys.zero_scalar_rows() == 40
+    assert abs(-39.09478965835833 - system.free_energy(0.1)) <= 1e-12 * 39.1      # the reference's value for this script
+    for T in (0.1, 0.5):
+        F = system.free_energy(T)
+        assert abs(system.free_energy(T, cuda=True) - F) <= 1e-10 * abs(F)
+    Fs = system.free_energy(0.1, cuda=True, vectors=4096, seed=3)   # sigma ~ 0.2 %; the zero rows' share is 3.5 %
+    assert abs(Fs - system.free_energy(0.1)) <= 1e-2 * abs(Fs)
